@@ -1,0 +1,4 @@
+"""Drop-in shim: put this directory on sys.path AHEAD of the reference checkout and the reference
+driver's `import Periodic` resolves to the B200 implementation."""
+from kmcislandgrowth_b200.Periodic import *  # noqa: F401,F403
+from kmcislandgrowth_b200.Periodic import _gv  # noqa: F401

@@ -1,0 +1,55 @@
+"""Builds libkmcb200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m kmcislandgrowth_b200.build [--force]
+
+The shared object is git-ignored but travels to the GPU box with the repository snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libkmcb200.so")
+SOURCES = ["kmc_b200.cu"]
+DEPS = ["kmc_b200.cu", "kmc_kernels.cuh", "kmc_device.cuh", os.path.join("..", "..", "include", "kmc_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+]
+
+
+def nvcc_path():
+    for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if p and (os.path.isabs(p) and os.path.exists(p) or not os.path.isabs(p)):
+            return p
+    return "nvcc"
+
+
+def up_to_date():
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(os.path.join(CSRC, d)) <= t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return OUT
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", OUT] + SOURCES
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    r = subprocess.run(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log = os.path.join(HERE, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout)
+    if verbose:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout[-4000:])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,552 @@
+// kmc_kernels.cuh -- the CUDA kernels of the hot path (sm_100a).
+//
+// Kernel families:
+//   bin_*      cell list build: cell ids (bit-exact BinIndex), counts, scan, scatter, per-cell order
+//   sweep_*    pair sweeps over the cell lists: forces, configuration energy (batched), rates
+//   probe      energies / closest distances of probe points (HoppingEnergy, DepositAdatom)
+//   select     sequential-order partial sums + first-greater search
+//   misc       wrap, distance matrix, list gathers, line-search candidates, relaxation control
+#pragma once
+#include "kmc_device.cuh"
+
+namespace kmc {
+
+// =============================================================================== cell lists
+
+// Bins.py:9-22 for n points -> (nx, ny)
+__global__ void k_bin_index(DevParams P, const double2* __restrict__ xy, int n, int2* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2 p = xy[i];
+    int nx, ny;
+    bin_index(P, p.x, p.y, nx, ny);
+    out[i] = make_int2(nx, ny);
+}
+
+// B configurations of n atoms: xy[b*n+i].  cell_of[b*n+i] = flat cell (ncell = outside); cnt[b*(ncell+2)+1+cell]++
+__global__ void k_bin_count(DevParams P, const double2* __restrict__ xy, int n, int B, int* __restrict__ cell_of,
+                            int* __restrict__ cnt) {
+    const int b = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double2 p = xy[(size_t)b * n + i];
+        int nx, ny;
+        bin_index(P, p.x, p.y, nx, ny);
+        const int c = flat_cell(P, nx, ny);
+        cell_of[(size_t)b * n + i] = c;
+        atomicAdd(&cnt[(size_t)b * (P.ncell + 2) + 1 + c], 1);
+    }
+}
+
+// in-place inclusive scan of cnt[b][1..ncell+1] (cnt[b][0] stays 0) -> start offsets; cursor = copy.
+// One CTA per configuration; chunked: each thread owns a contiguous chunk.
+__global__ void k_bin_scan(int ncell2 /* ncell+2 */, int* __restrict__ start, int* __restrict__ cursor) {
+    __shared__ int s_tot[1024];
+    const int b = blockIdx.x;
+    int* a = start + (size_t)b * ncell2;
+    int* cur = cursor + (size_t)b * ncell2;
+    const int m = ncell2 - 1;                         // entries 1..ncell+1
+    const int per = (m + blockDim.x - 1) / blockDim.x;
+    const int lo = 1 + threadIdx.x * per;
+    const int hi = min(lo + per, ncell2);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    s_tot[threadIdx.x] = sum;
+    __syncthreads();
+    // exclusive scan of the per-thread totals (Hillis-Steele in shared memory)
+    for (int off = 1; off < blockDim.x; off <<= 1) {
+        int v = (threadIdx.x >= off) ? s_tot[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_tot[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = s_tot[threadIdx.x] - sum;
+    for (int i = lo; i < hi; ++i) {
+        run += a[i];
+        a[i] = run;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncell2; i += blockDim.x) cur[i] = a[i];
+}
+
+// slot = cursor[cell]++ ; sidx[slot] = i   (order inside a cell fixed up by k_bin_order)
+__global__ void k_bin_scatter(int n, int B, int ncell2, const int* __restrict__ cell_of, int* __restrict__ cursor,
+                              int* __restrict__ sidx) {
+    const int b = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cell_of[(size_t)b * n + i];
+        const int slot = atomicAdd(&cursor[(size_t)b * ncell2 + c], 1);
+        sidx[(size_t)b * n + slot] = i;
+    }
+}
+
+// restore the reference's input order inside every cell (Bins.py:40-41 appends in input order) and
+// gather the positions.  One thread per cell: insertion sort for the usual ~10 atoms, heapsort beyond 32.
+__device__ inline void sort_indices(int* a, int m) {
+    if (m <= 32) {
+        for (int i = 1; i < m; ++i) {
+            int v = a[i], j = i - 1;
+            while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+            a[j + 1] = v;
+        }
+        return;
+    }
+    for (int start = m / 2 - 1; start >= 0; --start) {           // heapify
+        int root = start;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= m) break;
+            if (child + 1 < m && a[child] < a[child + 1]) ++child;
+            if (a[root] >= a[child]) break;
+            int t = a[root]; a[root] = a[child]; a[child] = t;
+            root = child;
+        }
+    }
+    for (int end = m - 1; end > 0; --end) {
+        int t = a[0]; a[0] = a[end]; a[end] = t;
+        int root = 0;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && a[child] < a[child + 1]) ++child;
+            if (a[root] >= a[child]) break;
+            int t2 = a[root]; a[root] = a[child]; a[child] = t2;
+            root = child;
+        }
+    }
+}
+
+__global__ void k_bin_order(int n, int B, int ncell2, const int* __restrict__ start, int* __restrict__ sidx,
+                            const double2* __restrict__ xy, double2* __restrict__ sxy) {
+    const int b = blockIdx.y;
+    const int* st = start + (size_t)b * ncell2;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell2 - 1; c += gridDim.x * blockDim.x) {
+        const int lo = st[c], hi = st[c + 1];
+        int* a = sidx + (size_t)b * n + lo;
+        sort_indices(a, hi - lo);
+        for (int s = lo; s < hi; ++s) sxy[(size_t)b * n + s] = xy[(size_t)b * n + sidx[(size_t)b * n + s]];
+    }
+}
+
+// =============================================================================== pair sweeps
+
+// accumulate the force of neighbour (xj,yj) on (xi,yi)
+__device__ __forceinline__ void acc_force(const DevParams& P, double xi, double yi, double2 pj, double E, double r0sq,
+                                          double& fx, double& fy) {
+    const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
+    const double dy = pj.y - yi;
+    const double r2 = dx * dx + dy * dy;
+    const double c = lj_force_coef(r2, E, r0sq);
+    fx += dx * c;
+    fy += dy * c;
+}
+
+__device__ __forceinline__ double pair_energy(const DevParams& P, double xi, double yi, double2 pj, double E, double r0sq) {
+    const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
+    const double dy = pj.y - yi;
+    return lj_energy(dx * dx + dy * dy, E, r0sq);
+}
+
+// Energy.py:62-75.  One group of G lanes per adatom (cell-sorted order so that a warp shares its
+// stencil); f_aa / f_as / f_sum are written at the atom's ORIGINAL index; any may be null.
+// `which_cfg` (device pointer, may be null) selects the configuration of a batch (line search winner).
+template <int G>
+__global__ void __launch_bounds__(256) k_sweep_forces(DevParams P, CellView ad_base, CellView sub, int n,
+                                                      const int* __restrict__ which_cfg, int ncell2,
+                                                      double2* __restrict__ f_aa, double2* __restrict__ f_as,
+                                                      double2* __restrict__ f_sum) {
+    const int cfg = which_cfg ? *which_cfg : 0;
+    CellView ad = ad_base;
+    if (ad.start) ad.start += (size_t)cfg * ncell2;
+    ad.sxy += (size_t)cfg * n;
+    if (ad.sidx) ad.sidx += (size_t)cfg * n;      // null sidx == identity order (aa_mode 0 needs no cell list)
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x & (G - 1);
+    const bool live = gid < n;
+    double ax = 0, ay = 0, sx = 0, sy = 0;
+    int idx = 0;
+    if (live) {
+        const double2 pi = ad.sxy[gid];
+        idx = ad.sidx ? ad.sidx[gid] : gid;
+        const Stencil st = make_stencil(P, pi.x, pi.y);
+        if (P.aa_mode == 0) {
+            for (int s = lane; s < n; s += G) acc_force(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2, ax, ay);
+        } else {
+            visit_stencil(P, ad, st, lane, G, [&](int s) { acc_force(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2, ax, ay); });
+        }
+        visit_stencil(P, sub, st, lane, G, [&](int s) { acc_force(P, pi.x, pi.y, sub.sxy[s], P.E_as, P.ras2, sx, sy); });
+    }
+    ax = group_sum<G>(ax); ay = group_sum<G>(ay);
+    sx = group_sum<G>(sx); sy = group_sum<G>(sy);
+    if (live && lane == 0) {
+        if (f_aa) f_aa[idx] = make_double2(ax, ay);
+        if (f_as) f_as[idx] = make_double2(sx, sy);
+        if (f_sum) f_sum[idx] = make_double2(ax + sx, ay + sy);     // 2DGrowth.py:120: F_aa + F_as
+    }
+}
+
+// Energy.py:133-148 for B configurations: E[b] = sum_i ( sum_{j visible from i, idx_j > idx_i} LJ_aa
+//                                                        + sum_{s in substrate stencil of i} LJ_as ).
+// grid = (blocks, B).  Deterministic: per-block partials, the last block of a configuration adds them
+// in block order.  done[b] must be zero on entry and is reset on exit.
+template <int G>
+__global__ void __launch_bounds__(256) k_sweep_energy(DevParams P, CellView ad_base, CellView sub, int n, int ncell2,
+                                                      double* __restrict__ partial, unsigned int* __restrict__ done,
+                                                      double* __restrict__ e_out) {
+    __shared__ double s_red[32];
+    __shared__ bool s_last;
+    const int b = blockIdx.y;
+    CellView ad = ad_base;
+    if (ad.start) ad.start += (size_t)b * ncell2;
+    ad.sxy += (size_t)b * n;
+    if (ad.sidx) ad.sidx += (size_t)b * n;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x & (G - 1);
+    double e = 0.0;
+    if (gid < n) {
+        const double2 pi = ad.sxy[gid];
+        const int idx = ad.sidx ? ad.sidx[gid] : gid;
+        const Stencil st = make_stencil(P, pi.x, pi.y);
+        if (P.aa_mode == 0) {
+            for (int s = lane; s < n; s += G)
+                if ((ad.sidx ? ad.sidx[s] : s) > idx) e += pair_energy(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2);
+        } else {
+            visit_stencil(P, ad, st, lane, G, [&](int s) {
+                if (ad.sidx[s] > idx) e += pair_energy(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2);
+            });
+        }
+        visit_stencil(P, sub, st, lane, G, [&](int s) { e += pair_energy(P, pi.x, pi.y, sub.sxy[s], P.E_as, P.ras2); });
+    }
+    const double tot = block_sum(e, s_red);
+    if (threadIdx.x == 0) {
+        partial[(size_t)b * gridDim.x + blockIdx.x] = tot;
+        __threadfence();
+        const unsigned int t = atomicAdd(&done[b], 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double v = 0.0;
+        if (threadIdx.x < 32) {
+            for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) v += partial[(size_t)b * gridDim.x + k];
+            v = group_sum<32>(v);
+            if (threadIdx.x == 0) { e_out[b] = v; done[b] = 0u; }
+        }
+    }
+}
+
+// Energy.py:121-131 TotalEnergy (unused by the driver, kept for API parity): quirky loop bounds.
+// Small-N utility: one block, all-pairs.
+__global__ void k_total_energy(DevParams P, const double2* __restrict__ xy, CellView sub, int n, double* __restrict__ e_out) {
+    __shared__ double s_red[32];
+    double e = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 pi = xy[i];
+        const bool in_loop = i < n - 2, last = (i == n - 1);
+        if (in_loop)
+            for (int j = i + 1; j < n; ++j) e += pair_energy(P, pi.x, pi.y, xy[j], P.E_a, P.ra2);
+        if (in_loop || last) {
+            const Stencil st = make_stencil(P, pi.x, pi.y);
+            visit_stencil(P, sub, st, 0, 1, [&](int s) { e += pair_energy(P, pi.x, pi.y, sub.sxy[s], P.E_as, P.ras2); });
+        }
+    }
+    const double tot = block_sum(e, s_red);
+    if (threadIdx.x == 0) e_out[0] = tot;
+}
+
+// Energy.py:174-217 + 2DGrowth.py:46-62,201-215 for every adatom.  Bond tests use the reference's exact
+// arithmetic (dist2_exact + IEEE sqrt) so that n_a / n_s / the surface flag agree bit for bit.
+template <int G>
+__global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellView ad, CellView sub, int n,
+                                                     double* __restrict__ rate, uint8_t* __restrict__ is_surface,
+                                                     double* __restrict__ delta_u, double* __restrict__ u_appx_o,
+                                                     double* __restrict__ u_loc_o, int* __restrict__ n_a_o,
+                                                     int* __restrict__ n_s_o) {
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x & (G - 1);
+    const bool live = gid < n;
+    double ua = 0, us = 0, la = 0, ls = 0;
+    int ka = 0, ks = 0, idx = 0;
+    if (live) {
+        const double2 pi = ad.sxy[gid];
+        idx = ad.sidx[gid];
+        const Stencil st = make_stencil(P, pi.x, pi.y);
+        if (P.aa_mode == 0)
+            for (int s = lane; s < n; s += G) ua += pair_energy(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2);
+        visit_stencil(P, ad, st, lane, G, [&](int s) {
+            const double2 pj = ad.sxy[s];
+            const double r2 = dist2_exact(P, pi.x, pi.y, pj.x, pj.y);
+            const double e = lj_energy(r2, P.E_a, P.ra2);
+            if (P.aa_mode != 0) ua += e;
+            if (sqrt(r2) < P.bond_a) { la += e; ++ka; }               // Bins.py:100 (the atom itself counts)
+        });
+        visit_stencil(P, sub, st, lane, G, [&](int s) {
+            const double2 pj = sub.sxy[s];
+            const double r2 = dist2_exact(P, pi.x, pi.y, pj.x, pj.y);
+            const double e = lj_energy(r2, P.E_as, P.ras2);
+            us += e;
+            if (sqrt(r2) < P.bond_s) { ls += e; ++ks; }               // Bins.py:107
+        });
+    }
+    ua = group_sum<G>(ua); us = group_sum<G>(us); la = group_sum<G>(la); ls = group_sum<G>(ls);
+    ka = group_sum_i<G>(ka); ks = group_sum_i<G>(ks);
+    if (live && lane == 0) {
+        const double appx = ua + us;                                  // Energy.py:181
+        const double loc = la + ls;                                   // Energy.py:192
+        const double ideal = -((double)ka * P.E_a + (double)ks * P.E_as);   // Energy.py:202
+        const double du = 1.0 * (loc - ideal) + appx;                 // Energy.py:217, C() = 1.0
+        const bool surf = (ka + ks) < 6;                              // 2DGrowth.py:59
+        if (rate) rate[idx] = surf ? P.omega * exp(du * P.beta) : 0.0;   // 2DGrowth.py:215
+        if (is_surface) is_surface[idx] = surf ? 1 : 0;
+        if (delta_u) delta_u[idx] = du;
+        if (u_appx_o) u_appx_o[idx] = appx;
+        if (u_loc_o) u_loc_o[idx] = loc;
+        if (n_a_o) n_a_o[idx] = ka;
+        if (n_s_o) n_s_o[idx] = ks;
+    }
+}
+
+// Energy.py:170-172 / :77-95 and the closeness test of 2DGrowth.py:82-90.  One warp per probe point.
+__global__ void __launch_bounds__(128) k_probe(DevParams P, const double2* __restrict__ probes, int m, CellView ad, CellView sub,
+                                               double* __restrict__ e_aa, double* __restrict__ e_as,
+                                               double* __restrict__ min_d_a, double* __restrict__ min_d_s) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool live = w < m;
+    double ea = 0, es = 0, da = INFINITY, ds = INFINITY;
+    if (live) {
+        const double2 pi = probes[w];
+        const Stencil st = make_stencil(P, pi.x, pi.y);
+        if (ad.n > 0) {
+            if (P.aa_mode == 0)
+                for (int s = lane; s < ad.n; s += 32) ea += pair_energy(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2);
+            visit_stencil(P, ad, st, lane, 32, [&](int s) {
+                const double2 pj = ad.sxy[s];
+                const double r2 = dist2_exact(P, pi.x, pi.y, pj.x, pj.y);
+                if (P.aa_mode != 0) ea += lj_energy(r2, P.E_a, P.ra2);
+                da = fmin(da, sqrt(r2));
+            });
+        }
+        visit_stencil(P, sub, st, lane, 32, [&](int s) {
+            const double2 pj = sub.sxy[s];
+            const double r2 = dist2_exact(P, pi.x, pi.y, pj.x, pj.y);
+            es += lj_energy(r2, P.E_as, P.ras2);
+            ds = fmin(ds, sqrt(r2));
+        });
+    }
+    ea = group_sum<32>(ea); es = group_sum<32>(es);
+    da = group_min<32>(da); ds = group_min<32>(ds);
+    if (live && lane == 0) {
+        if (e_aa) e_aa[w] = ea;
+        if (e_as) e_as[w] = es;
+        if (min_d_a) min_d_a[w] = da;
+        if (min_d_s) min_d_s[w] = ds;
+    }
+}
+
+// =============================================================================== selection
+
+// 2DGrowth.py:217-227,322-329.  The partial sums are formed strictly left to right like the
+// reference's sum(Rk[:i+1]) so that every pj -- and therefore the selected index -- is bit-identical
+// for the same rates and the same u.  One warp: lanes prefetch 32 rates, lane 0 owns the running sum.
+// result[0] = compacted k or -1 ; result[1] = dense index or -1 ; rtot[0] = Rd + sum.
+__global__ void k_select(DevParams P, const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, double u,
+                         long long* __restrict__ result, double* __restrict__ rtot, double* __restrict__ pj_out) {
+    const int lane = threadIdx.x;
+    // pass 1: total in reference order
+    double sum = 0.0;
+    for (int base = 0; base < n; base += 32) {
+        const double v = (base + lane < n) ? rate[base + lane] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const double vk = __shfl_sync(0xffffffffu, v, k);
+            sum = __dadd_rn(sum, vk);                       // identical in every lane
+        }
+    }
+    const double Rtot = __dadd_rn(P.Rd, sum);               // 2DGrowth.py:227
+    const double r = __dmul_rn(u, Rtot);                    // 2DGrowth.py:322
+    // pass 2: first partial sum > r
+    double pj = 0.0;
+    int found = -1, kcomp = 0, kfound = -1;
+    if (pj_out && lane == 0) pj_out[0] = 0.0;
+    for (int base = 0; base < n && (found < 0 || pj_out); base += 32) {
+        const double v = (base + lane < n) ? rate[base + lane] : 0.0;
+        const int sf = (base + lane < n) ? (int)surf[base + lane] : 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const double vk = __shfl_sync(0xffffffffu, v, k);
+            const int sk = __shfl_sync(0xffffffffu, sf, k);
+            if (base + k < n) {
+                pj = __dadd_rn(pj, vk);
+                if (pj_out && lane == 0) pj_out[base + k + 1] = pj;
+                if (found < 0 && sk) {
+                    if (pj > r) { found = base + k; kfound = kcomp; }
+                    ++kcomp;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        result[0] = kfound;
+        result[1] = found;
+        rtot[0] = Rtot;
+    }
+}
+
+// =============================================================================== misc
+
+// Periodic.py:22-25
+__global__ void k_put_all_in_box(DevParams P, double2* __restrict__ xy, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) xy[i].x = put_in_box(xy[i].x, P.L, P.halfL);
+}
+
+// Periodic.py:54-62
+__global__ void k_distances(DevParams P, const double2* __restrict__ a, int na, const double2* __restrict__ b, int nb,
+                            double* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)na * nb) return;
+    const int i = (int)(t / nb), j = (int)(t % nb);
+    out[t] = sqrt(dist2_exact(P, a[i].x, a[i].y, b[j].x, b[j].y));
+}
+
+// Periodic.py:27-36
+__global__ void k_displacement(DevParams P, const double2* __restrict__ ri, const double2* __restrict__ rj, int k,
+                               double2* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    out[i] = make_double2(put_in_box(__dadd_rn(rj[i].x, -ri[i].x), P.L, P.halfL), __dadd_rn(rj[i].y, -ri[i].y));
+}
+
+// Bins.py:72-84: stencil populations of nq query points
+__global__ void k_nearby_count(DevParams P, CellView cv, const double2* __restrict__ q, int nq, long long* __restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    counts[i + 1] = stencil_population(P, cv, make_stencil(P, q[i].x, q[i].y));
+    if (i == 0) counts[0] = 0;
+}
+
+// in-place inclusive scan of a[1..m] (a[0] = 0), single block (list lengths, not a hot path)
+__global__ void k_scan_i64(long long* __restrict__ a, int m) {
+    __shared__ long long s_tot[1024];
+    const int per = (m + blockDim.x - 1) / blockDim.x;
+    const int lo = 1 + threadIdx.x * per, hi = min(lo + per, m + 1);
+    long long sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    s_tot[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < blockDim.x; off <<= 1) {
+        long long v = (threadIdx.x >= off) ? s_tot[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_tot[threadIdx.x] += v;
+        __syncthreads();
+    }
+    long long run = s_tot[threadIdx.x] - sum;
+    for (int i = lo; i < hi; ++i) { run += a[i]; a[i] = run; }
+}
+
+__global__ void k_nearby_fill(DevParams P, CellView cv, const double2* __restrict__ q, int nq,
+                              const long long* __restrict__ offs, long long cap, double2* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    long long o = offs[i];
+    const Stencil st = make_stencil(P, q[i].x, q[i].y);
+    visit_stencil(P, cv, st, 0, 1, [&](int s) {
+        if (o < cap) out[o] = cv.sxy[s];
+        ++o;
+    });
+}
+
+// Bins.py:86-111 position lists, reference order; which: 0 adatom bonds, 1 substrate bonds
+__global__ void k_neighbor_fill(DevParams P, const double2* __restrict__ xy, int n, CellView cv, double bond,
+                                const long long* __restrict__ offs, long long cap, double2* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 pi = xy[i];
+    long long o = offs[i];
+    const Stencil st = make_stencil(P, pi.x, pi.y);
+    visit_stencil(P, cv, st, 0, 1, [&](int s) {
+        const double2 pj = cv.sxy[s];
+        if (sqrt(dist2_exact(P, pi.x, pi.y, pj.x, pj.y)) < bond) {
+            if (o < cap) out[o] = pj;
+            ++o;
+        }
+    });
+}
+
+__global__ void k_i32_to_offsets(const int* __restrict__ counts, int n, long long* __restrict__ offs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) offs[i + 1] = counts[i];
+    if (i == 0) offs[0] = 0;
+}
+
+// 2DGrowth.py:121,152: cand[a][i] = x[i] + a*s[i]/20/scale (same operation order: ((a*s)/20)/scale)
+__global__ void k_make_candidates(const double* __restrict__ x, const double* __restrict__ s, int n2, int K, double scale,
+                                  double* __restrict__ cand) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y;
+    if (i >= n2 || a >= K) return;
+    cand[(size_t)a * n2 + i] = __dadd_rn(x[i], __ddiv_rn(__ddiv_rn(__dmul_rn((double)a, s[i]), 20.0), scale));
+}
+
+// ---- relaxation control (2DGrowth.py:97-166) ----------------------------------------------------
+struct RelaxCtrl {
+    double maxF, miny, top, bot;   // reductions of the current iterate
+    int amin;                      // winning candidate of the last line search
+    int pad;
+};
+
+// first argmin of K energies (ys.index(min(ys)), 2DGrowth.py:123,155)
+__global__ void k_argmin(const double* __restrict__ e, int K, RelaxCtrl* __restrict__ ctrl) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int am = 0;
+        double em = e[0];
+        for (int a = 1; a < K; ++a)
+            if (e[a] < em) { em = e[a]; am = a; }
+        ctrl->amin = am;
+    }
+}
+
+// after the forces at xnp = cand[amin]: maxF = max_i |F_i|^2 (:129,160), miny (:137), top = xnp.(xnp-xn),
+// bot = xn.xn (:143-144).  Also copies xnp out of the candidate batch.  Single block (deterministic).
+__global__ void k_relax_reduce(const double* __restrict__ cand, const double* __restrict__ xn, const double2* __restrict__ F,
+                               int n, RelaxCtrl* __restrict__ ctrl, double* __restrict__ xnp) {
+    __shared__ double s_red[32];
+    const double* xc = cand + (size_t)ctrl->amin * 2 * n;
+    double mf = 0.0, my = INFINITY, top = 0.0, bot = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 f = F[i];
+        mf = fmax(mf, f.x * f.x + f.y * f.y);
+        const double x = xc[2 * i], y = xc[2 * i + 1];
+        const double x0 = xn[2 * i], y0 = xn[2 * i + 1];
+        my = fmin(my, y);
+        top += x * (x - x0) + y * (y - y0);
+        bot += x0 * x0 + y0 * y0;
+        xnp[2 * i] = x;
+        xnp[2 * i + 1] = y;
+    }
+    const double r_mf = block_max(mf, s_red);
+    const double r_my = block_min(my, s_red);
+    const double r_top = block_sum(top, s_red);
+    const double r_bot = block_sum(bot, s_red);
+    if (threadIdx.x == 0) { ctrl->maxF = r_mf; ctrl->miny = r_my; ctrl->top = r_top; ctrl->bot = r_bot; }
+}
+
+// snp = dxnp + beta*sn ; xn = xnp ; sn = snp  (2DGrowth.py:147-150)
+__global__ void k_cg_update(const double* __restrict__ F, double beta, double* __restrict__ sn, double* __restrict__ xn,
+                            const double* __restrict__ xnp, int n2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    sn[i] = __dadd_rn(F[i], __dmul_rn(beta, sn[i]));
+    xn[i] = xnp[i];
+}
+
+__global__ void k_min_y(const double2* __restrict__ xy, int n, int want_max, double* __restrict__ out) {
+    __shared__ double s_red[32];
+    double v = want_max ? -INFINITY : INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v = want_max ? fmax(v, xy[i].y) : fmin(v, xy[i].y);
+    const double r = want_max ? block_max(v, s_red) : block_min(v, s_red);
+    if (threadIdx.x == 0) out[0] = r;
+}
+
+}  // namespace kmc

@@ -1,0 +1,294 @@
+"""GPU parity: the CUDA path (through the C-ABI / drop-in modules) against the golden vectors the
+reference produced (tests/golden/) and against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): energies, forces, rates within 1e-6 relative in fp64 (we
+assert 1e-9 .. 1e-10, the measured agreement is ~1e-14); bin ids, stencils, bond counts, surface
+flags and the selected event index bit-exact.  Forces are compared against the force scale
+max|F| (net forces are differences of eV/A-sized pair terms).
+"""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["default", "w24misfit", "w20"]
+
+
+@pytest.fixture(autouse=True)
+def _fresh_constants():
+    from kmcislandgrowth_b200 import Constants
+    yield
+    Constants.configure()
+
+
+def setup_case(name):
+    from kmcislandgrowth_b200 import Constants
+    z = np.load(os.path.join(GOLDEN, "static_%s.npz" % name))
+    meta = json.load(open(os.path.join(GOLDEN, "static_%s.json" % name)))
+    c = meta["constants"]
+    Constants.configure(c["E_a"], c["E_s"], c["r_a"], c["r_s"], c["W"])
+    return z, meta, c
+
+
+def relerr(a, b, floor=1e-300):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0 and b.size == 0:
+        return 0.0
+    assert a.shape == b.shape
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_periodic_golden(name):
+    from kmcislandgrowth_b200 import Periodic
+    z, meta, c = setup_case(name)
+    got = np.array([Periodic.PutInBox(x) for x in z["putinbox_in"][:12]])
+    assert np.array_equal(got, z["putinbox_out"][:12])
+    R = np.column_stack([z["putinbox_in"], z["putinbox_in"]]).reshape(-1).copy()
+    ret = Periodic.PutAllInBox(R)
+    assert ret is R                                           # in place, returns its argument
+    assert np.array_equal(R[0::2], z["putinbox_out"])         # bit-exact wrap
+    assert np.array_equal(R[1::2], z["putinbox_in"])          # y untouched
+    assert relerr(Periodic.Distances(z["dist_a"], z["dist_b"]), z["dist_out"]) < 1e-15
+    a = z["dist_a"]
+    assert np.array_equal(Periodic.Displacement(a, a[::-1].copy()), z["disp_out"])
+    assert np.array_equal(Periodic.Displacements(float(a[0]), float(a[1]), z["dist_b"]), z["displs_out"])
+    assert relerr([Periodic.Distance(a[0:2], z["dist_b"][2 * j:2 * j + 2]) for j in range(9)], z["distance_out"]) < 1e-15
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_bins_golden(name):
+    from kmcislandgrowth_b200 import Bins, Energy, Growth, runtime
+    z, meta, c = setup_case(name)
+    pts = np.column_stack([z["bin_px"], z["bin_py"]]).reshape(-1)
+    got = runtime.context().bin_index(pts)
+    assert np.array_equal(got, z["binindex_out"])             # bit-exact BinIndex
+    xo = z["nearbybins_xoff"]
+    for i in range(0, len(z["bin_px"]), 7):
+        xs, ys = Bins.NearbyBins(z["bin_px"][i], z["bin_py"][i])
+        assert xs == list(z["nearbybins_x"][xo[i]:xo[i + 1]])
+        assert ys == list(z["nearbybins_y"][3 * i:3 * i + 3])
+    sub = Growth.InitSubstrate()
+    assert np.array_equal(sub, z["substrate"])
+    sb = Bins.PutInBins(sub)
+    # cell contents identical to the reference's ragged lists, in the same order
+    rows, offs, vals = z["sbins_rows"], z["sbins_offs"], z["sbins_vals"]
+    k = 0
+    for cx in range(len(rows)):
+        col = sb[cx] if cx < c["nbins_x"] else None
+        for cy in range(rows[cx]):
+            want = vals[offs[k]:offs[k + 1]]
+            if col is not None and cy < c["nbins_y"]:
+                have = np.asarray(col[cy]) if cy < len(col) else np.zeros(0)
+                assert np.array_equal(have, want), (cx, cy)
+            k += 1
+    # NearbyAtoms: same atoms, same order; all queries in one launch as well
+    no = z["nearby_offs"]
+    q = np.column_stack([z["nearby_qx"], z["nearby_qy"]]).reshape(-1)
+    out, o2 = runtime.context().nearby_atoms(sb.handle(), q)
+    assert np.array_equal(o2 * 2, no) and np.array_equal(out, z["nearby_vals"])
+    assert np.array_equal(Bins.NearbyAtoms(q[0], q[1], sb), z["nearby_vals"][no[0]:no[1]])
+    e = np.array([Energy.AdatomSurfaceEnergy(q[2 * i:2 * i + 2], sb) for i in range(0, len(q) // 2, 5)])
+    assert relerr(e, z["surf_energy_q"][::5]) < 1e-12
+    assert np.allclose(Energy.AdatomSubstrateForces(q, sb), z["as_forces_q"], rtol=1e-10, atol=1e-13)
+
+
+def _sets():
+    out = []
+    for name in CASES:
+        meta = json.load(open(os.path.join(GOLDEN, "static_%s.json" % name)))
+        for s in meta["sets"]:
+            out.append((name, s["key"], bool(s.get("rates"))))
+    return out
+
+
+@pytest.mark.parametrize("name,key,has_rates", _sets())
+def test_energy_golden(name, key, has_rates):
+    from kmcislandgrowth_b200 import Bins, Energy, Growth, runtime
+    z, meta, c = setup_case(name)
+    sb = Bins.PutInBins(z["substrate"])
+    ad = z[key + "_ad"]
+    n = ad.size // 2
+    fscale = max(1.0, float(np.max(np.abs(z[key + "_faa"]))), float(np.max(np.abs(z[key + "_fas"]))))
+    assert np.max(np.abs(Energy.AdatomAdatomForces(ad) - z[key + "_faa"])) < 1e-10 * fscale
+    assert np.max(np.abs(Energy.AdatomSubstrateForces(ad, sb) - z[key + "_fas"])) < 1e-10 * fscale
+    assert np.max(np.abs(Energy.TotalForces(ad, sb) - (z[key + "_faa"] + z[key + "_fas"]))) < 1e-10 * fscale
+    assert abs(Energy.RelaxEnergy((ad, sb)) - z[key + "_relax_energy"]) < 1e-11 * abs(z[key + "_relax_energy"])
+    assert abs(Energy.TotalEnergy(ad, sb) - z[key + "_total_energy"]) <= 1e-11 * max(1.0, abs(z[key + "_total_energy"]))
+    # the 20 line-search candidates: host-formed batch (pool.map replacement) and device-formed
+    dx0 = z[key + "_faa"] + z[key + "_fas"]
+    xs = [(ad + a * dx0 / 20 / 16, sb) for a in range(20)]
+    ls = np.array(Energy.RelaxEnergyBatch(xs))
+    assert relerr(ls, z[key + "_ls_energies"]) < 1e-11
+    assert int(np.argmin(ls)) == int(np.argmin(z[key + "_ls_energies"]))
+    ls2 = runtime.context().line_energies(ad, dx0, sb.handle(), 16, 20)
+    assert relerr(ls2, z[key + "_ls_energies"]) < 1e-11
+    pr = z[key + "_probes"].reshape(-1, 2)
+    assert relerr(Energy.HoppingEnergies(pr, ad, sb), z[key + "_hop_energy"]) < 1e-11
+    assert abs(Energy.HoppingEnergy(pr[0], ad, sb) - z[key + "_hop_energy"][0]) < 1e-11 * abs(z[key + "_hop_energy"][0])
+    # bond lists: same positions in the same order (bit-exact)
+    nn_a, nn_s = Bins.NearestNeighbors(ad, sb)
+    ao, so = z[key + "_nn_a_offs"], z[key + "_nn_s_offs"]
+    for i in range(n):
+        assert np.array_equal(nn_a[i], z[key + "_nn_a_vals"][ao[i]:ao[i + 1]])
+        assert np.array_equal(nn_s[i], z[key + "_nn_s_vals"][so[i]:so[i + 1]])
+    assert np.array_equal(Growth.SurfaceAtoms(ad, sb), z[key + "_surface_pos"])
+    if has_rates:
+        sidx = z[key + "_surface_idx"]
+        b = Energy.Barriers(ad, sb)
+        assert np.array_equal(np.nonzero(b["is_surface"])[0], sidx)
+        assert relerr(b["u_appx"][sidx], z[key + "_uappx"]) < 1e-11
+        assert np.max(np.abs(b["u_loc"][sidx] - z[key + "_uloc"])) < 1e-11
+        assert np.max(np.abs(b["delta_u"][sidx] - z[key + "_deltaU"])) < 1e-10
+        assert relerr(b["rate"][sidx], z[key + "_rates"]) < 1e-8
+        Rk = Growth.HoppingRates(ad, sb)
+        assert relerr(Rk, z[key + "_rates"]) < 1e-8
+        if len(sidx):
+            i0 = int(sidx[0])
+            assert abs(Energy.DeltaU(i0, ad, sb) - z[key + "_deltaU"][0]) < 1e-10
+            assert Energy.U_loc_ideal(i0, ad, sb) == z[key + "_uideal"][0]
+        # partial sums and selection on the REFERENCE's rates: bit-exact
+        ref_rates = z[key + "_rates"]
+        assert np.array_equal(np.array(Growth.HoppingPartialSums(ref_rates)), z[key + "_pj"])
+        assert Growth.TotalRate(float(z[key + "_Rd"]), ref_rates) == float(z[key + "_Rtot"])
+        dense = np.zeros(n)
+        dense[sidx] = ref_rates
+        flags = np.zeros(n, dtype=np.uint8)
+        flags[sidx] = 1
+        ctx = runtime.context()
+        for u, want in zip(z[key + "_sel_u"][::4], z[key + "_sel_idx"][::4]):
+            k, didx, rtot = ctx.select(dense, flags, u)
+            assert k == want and rtot == z[key + "_Rtot"]
+            if k >= 0:
+                assert didx == sidx[k]
+
+
+def test_relaxation_trace_golden():
+    """One full Relaxation (2DGrowth.py:97-166): same line-search count as the reference, same result."""
+    from kmcislandgrowth_b200 import Bins, Growth
+    z = np.load(os.path.join(GOLDEN, "relax_trace.npz"))
+    sb = Bins.PutInBins(Growth.InitSubstrate())
+    stats = []
+    x = Growth.Relaxation(z["ad0"], sb, stats=stats)
+    assert stats[0].status == 0
+    assert np.max(np.abs(x - z["result"])) < 1e-6
+    assert stats[0].line_searches == z["energies"].shape[0]
+
+
+def test_trajectory_golden():
+    """The reference's seeded KMC loop, event by event from the reference's own states."""
+    from kmcislandgrowth_b200 import Growth
+    z = np.load(os.path.join(GOLDEN, "trajectory.npz"))
+    us, offs, vals = z["uniforms"], z["states_offs"], z["states_vals"]
+    sim = Growth.Simulation()
+    pos = 0
+    report = []
+    for t in range(len(z["kinds"])):
+        prev = vals[offs[t - 1]:offs[t]] if t > 0 else np.zeros(0)
+        nls_ref = int(z["line_searches"][t])
+        sim.set_adatoms(prev)
+        rec = sim.step(us[pos], us[pos + 1], max_line_searches=0 if nls_ref < 2000 else 3000)
+        pos = int(z["uniforms_used"][t])
+        assert rec["kind"] == z["kinds"][t] and rec["hop_k"] == z["hop_idx"][t], t
+        assert abs(rec["rtot"] - z["rtot"][t]) <= 1e-9 * abs(z["rtot"][t])
+        want = vals[offs[t]:offs[t + 1]]
+        got = sim.adatoms
+        assert got.size == want.size
+        if nls_ref < 2000:      # the one 41k-line-search event is chaotic: only its start is checked
+            err = float(np.max(np.abs(got - want)))
+            report.append((t, nls_ref, rec["line_searches"], err))
+            assert err < 1e-5, report
+            assert rec["line_searches"] == nls_ref, report
+    sim.close()
+
+
+def _oracle_for(gv):
+    p = orc.make_params(gv.E_a, gv.E_s, gv.r_a, gv.r_s, gv.W, gv.Hs, gv.Ha, gv.temperature, gv.deposition_rate,
+                        aa_mode=gv.aa_mode, hop_index_mode=gv.hop_index_mode, deposit_mode=gv.deposit_mode)
+    return orc.Oracle(p)
+
+
+@pytest.mark.parametrize("W,Hs,Ha,n,aa", [(18, 10, 10, 150, 1), (48, 12, 10, 700, 0), (48, 12, 10, 700, 1),
+                                          (64, 16, 16, 1500, 1), (256, 256, 64, 10000, 1)])
+def test_vs_oracle_sizes(W, Hs, Ha, n, aa):
+    """bins3x3 / all-pairs modes against the oracle on seeded films up to BASELINE config 2's full size."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(W, Hs, Ha, aa_mode=aa)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, n, seed=W + n)
+    o = _oracle_for(gv)
+    osb = o.PutInBins(sub)
+    ctx = runtime.Context(runtime.params_from(gv), 0)
+    sb = ctx.bins_create(sub)
+    try:
+        # bin ids bit-exact
+        ab = ctx.bins_create(ad)
+        cell = ctx.bins_export(ab)[0]
+        ocell = o.PutInBins(ad).cell_of_atom()
+        ncell = gv.nbins_x * gv.nbins_y
+        assert np.array_equal(np.where(cell == ncell, -1, cell), ocell)
+        ab.close()
+        Fo = o.AdatomAdatomForces(ad) + o.AdatomSubstrateForces(ad, osb)
+        F = ctx.forces(ad, sb, 3)
+        assert np.max(np.abs(F - Fo)) < 1e-9 * max(1.0, np.max(np.abs(Fo)))
+        eo = o.RelaxEnergy((ad, osb))
+        assert abs(ctx.relax_energy(ad, sb)[0] - eo) < 1e-10 * abs(eo)
+        # 20 candidates
+        ls = ctx.line_energies(ad, F, sb, 16, 20)
+        lso = np.array([o.RelaxEnergy((ad + a * Fo / 20 / 16, osb)) for a in range(0, 20, 7)])
+        assert relerr(ls[::7], lso) < 1e-10
+        r = ctx.rates(ad, sb)
+        rate_o, surf_o, du_o = o.HoppingRatesDense(ad, osb)
+        ua, ul, ui, du, na, ns = o.Barriers(ad, osb)
+        assert np.array_equal(r["n_a"], na) and np.array_equal(r["n_s"], ns)
+        assert np.array_equal(r["is_surface"].astype(bool), surf_o)
+        assert np.max(np.abs(r["delta_u"] - du_o)) < 1e-9 * max(1.0, np.max(np.abs(du_o)))
+        assert relerr(r["rate"][surf_o], rate_o[surf_o]) < 1e-7
+        for u in (0.0, 0.123, 0.5, 0.999999):
+            assert ctx.select(rate_o, surf_o.astype(np.uint8), u) == o.Select(rate_o, u)
+    finally:
+        sb.close()
+        ctx.close()
+
+
+def test_edge_cases():
+    """empty / single-atom inputs and atoms outside the cell grid"""
+    from kmcislandgrowth_b200 import Bins, Energy, Growth, Periodic, runtime
+    sb = Bins.PutInBins(Growth.InitSubstrate())
+    assert Energy.AdatomAdatomForces(np.array([])).size == 0
+    assert Energy.RelaxEnergy((np.array([]), sb)) == 0
+    assert Growth.HoppingRates(np.array([]), sb) == []
+    assert Growth.SurfaceAtoms(np.array([]), sb).size == 0
+    assert Periodic.Distances(np.array([]), np.array([1.0, 2.0])).size == 0
+    o = orc.Oracle()
+    osb = o.PutInBins(orc.init_substrate(18, 10, 2.7, 48.6))
+    one = np.array([3.3, 2.5])
+    assert abs(Energy.RelaxEnergy((one, sb)) - o.RelaxEnergy((one, osb))) < 1e-12
+    assert np.allclose(Energy.TotalForces(one, sb), o.AdatomSubstrateForces(one, osb), rtol=1e-11)
+    # unwrapped line-search candidates: x beyond +-L/2 and y above the grid (Bins.py:60-65 single wrap)
+    ad = np.array([24.35, 2.4, -24.4, 2.4, 0.0, 2.4, 2.7, 2.4, 5.0, 34.0, 7.0, 36.0])
+    e, eo = Energy.RelaxEnergy((ad, sb)), o.RelaxEnergy((ad, osb))
+    assert abs(e - eo) < 1e-11 * abs(eo)
+    F = Energy.TotalForces(ad, sb)
+    Fo = o.AdatomAdatomForces(ad) + o.AdatomSubstrateForces(ad, osb)
+    assert np.max(np.abs(F - Fo)) < 1e-10 * max(1.0, np.max(np.abs(Fo)))
+    b = Energy.Barriers(ad, sb)
+    ua, ul, ui, du, na, ns = o.Barriers(ad, osb)
+    assert np.array_equal(b["n_a"], na) and np.array_equal(b["n_s"], ns)
+    assert np.max(np.abs(b["delta_u"] - du)) < 1e-10
+    # bins3x3 mode with atoms outside the grid (invisible as neighbours, Bins.py:24-42 + :57-65)
+    from kmcislandgrowth_b200 import Constants
+    Constants.aa_mode = 1
+    try:
+        o1 = orc.Oracle(aa_mode=1)
+        e1 = Energy.RelaxEnergy((ad, sb))
+        eo1 = o1.RelaxEnergy((ad, o1.PutInBins(orc.init_substrate(18, 10, 2.7, 48.6))))
+        assert abs(e1 - eo1) < 1e-11 * abs(eo1)
+    finally:
+        del Constants.aa_mode
