@@ -2,6 +2,7 @@
 // See include/kmc_b200.h for the contract of every entry point and the reference lines it replaces.
 #include "../../include/kmc_b200.h"
 #include "kmc_kernels.cuh"
+#include "kmc_line.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -80,7 +81,8 @@ struct KmcCtx {
 enum Slot {
     S_IN0 = 0, S_IN1, S_IN2, S_IN3, S_OUT0, S_OUT1, S_OUT2, S_OUT3, S_OUT4, S_OUT5, S_OUT6, S_OUT7,
     S_CELLOF, S_START, S_CURSOR, S_SXY, S_SIDX, S_PARTIAL, S_DONE, S_CAND, S_E, S_CTRL,
-    S_F, S_FAA, S_FAS, S_X0, S_XN, S_XNP, S_SN, S_TMP0, S_TMP1, S_TMP2, S_TMP3, S_COUNT
+    S_F, S_FAA, S_FAS, S_X0, S_XN, S_XNP, S_SN, S_TMP0, S_TMP1, S_TMP2, S_TMP3,
+    S_FLAG, S_MOVERS, S_NMOV, S_LPART, S_FIX, S_AMIN, S_COUNT
 };
 
 static int ensure(KmcCtx* c, DBuf& b, size_t bytes) {
@@ -292,6 +294,28 @@ static int energy_dev(KmcCtx* c, CellView ad, const KmcBins* sb, int n, int B, d
         case 8: LAUNCH(c, "sweep_energy", k_sweep_energy<8>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e); break;
         default: LAUNCH(c, "sweep_energy", k_sweep_energy<4>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e); break;
     }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// 2DGrowth.py:121-122,152-153: energies of the KC = 20 candidates x + a*s/20/scale from one base cell list
+// (`ad` = cell list of x).  d_e[KC] and *d_amin (first argmin) are device pointers; d_amin may be null.
+static const int LINE_BLOCKS = 148 * 8;
+static int line_energies_dev(KmcCtx* c, const double2* d_x, const double2* d_s, int n, double scale, CellView ad, const KmcBins* sb,
+                             double* d_e, int* d_amin) {
+    LineArgs A{};
+    A.P = c->dp; A.ad = ad; A.sub = view_of(sb); A.x = d_x; A.s = d_s; A.scale = scale; A.inv_step = 1.0 / (20.0 * scale); A.n = n;
+    TRY(slot(c, S_FLAG, (size_t)n, &A.flag));
+    TRY(slot(c, S_MOVERS, (size_t)n, &A.movers));
+    TRY(slot(c, S_NMOV, 4, &A.n_movers));
+    TRY(slot(c, S_LPART, (size_t)LINE_BLOCKS * KC, &A.partial));
+    TRY(slot(c, S_FIX, (size_t)n * KC, &A.fix));
+    A.e_out = d_e; A.amin_out = d_amin;
+    LAUNCH(c, "line_mark", k_line_mark, std::min(cdiv(n, 256), 1184u), 256, A);
+    LAUNCH(c, "line_compact", k_line_compact, 1, 1024, A);
+    LAUNCH(c, "line_energy", k_line_energy, LINE_BLOCKS, LT_THREADS, A);
+    LAUNCH(c, "line_fix", k_line_fix, 296, 128, A);
+    LAUNCH(c, "line_reduce", k_line_reduce, 1, KC * 32, A, LINE_BLOCKS);
     CK(cudaGetLastError());
     return 0;
 }
@@ -658,6 +682,12 @@ int kmc_line_energies(KmcCtx* c, const double* xy, const double* dir, int64_t n,
     TRY(call.in(xy, (size_t)2 * n, S_IN0, &dx));
     TRY(call.in(dir, (size_t)2 * n, S_IN1, &ds));
     TRY(call.out(e_out, (size_t)K, S_OUT0, &de));
+    if (K == KC && n > 0) {      // the line-search engine: one cell list, 20 candidates per pair in registers
+        CellView ad;
+        TRY(scratch_cells(c, (const double2*)dx, (int)n, 1, &ad));
+        TRY(line_energies_dev(c, (const double2*)dx, (const double2*)ds, (int)n, (double)scale, ad, sb, de, nullptr));
+        return call.finish();
+    }
     TRY(slot(c, S_CAND, (size_t)2 * n * K, &cand));
     if (n > 0) {
         dim3 g(cdiv(2 * n, 256), K);

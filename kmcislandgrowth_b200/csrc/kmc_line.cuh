@@ -1,0 +1,360 @@
+// kmc_line.cuh -- the line-search engine: energies of the 20 candidates x + a*s/20/scale
+// (2DGrowth.py:121-122,152-153) from ONE cell list, every pair evaluated once with its 20 candidate
+// energies held in registers.
+//
+// Exactness.  RelaxEnergy (Energy.py:133-148) is a pure function of the candidate positions: the
+// substrate stencil of an adatom -- and in bins3x3 mode the adatom pairs that are counted -- depend on
+// the CELLS of the candidate positions.  Along one line x + a*delta every coordinate is monotone in a,
+// so an atom whose raw cell is the same (and inside the grid) at a = 0 and a = K-1 keeps it for every
+// candidate.  Those atoms take the fast path below (stencil membership fixed by the base cell list);
+// the others ("movers", typically none to a few dozen) are evaluated per candidate with their own
+// stencils by k_line_fix, reproducing the per-candidate semantics exactly, including atoms that leave
+// the addressable grid and become invisible to others (Bins.py:24-42,57-65).
+#pragma once
+#include "kmc_device.cuh"
+
+namespace kmc {
+
+constexpr int KC = 20;        // candidates per line search: range(20) at 2DGrowth.py:121,152
+constexpr int LT_HOME = 64;   // home atoms staged per pass
+constexpr int LT_TILE = 256;  // neighbour atoms staged per pass
+constexpr int LT_THREADS = 128;
+
+// candidate a of coordinate v moving along s: v + ((a*s)/20)/scale, the reference's operation order
+__device__ __forceinline__ double cand1(double v, double s, int a, double scale) {
+    return __dadd_rn(v, __ddiv_rn(__ddiv_rn(__dmul_rn((double)a, s), 20.0), scale));
+}
+__device__ __forceinline__ double2 cand2(double2 p, double2 s, int a, double scale) {
+    return make_double2(cand1(p.x, s.x, a, scale), cand1(p.y, s.y, a, scale));
+}
+
+// 1/x to ~1 ulp: MUFU.RCP64H seed (2^-23) + two Newton steps (no IEEE corner cases needed: x is a
+// squared distance, finite and > 0 where the result is used)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+// energies of one pair for all KC candidates: displacement d0 + a*dd (d0 already min-image wrapped).
+// Stable pairs (the wrap cannot change along the line) use r^2(a) = A + a(B + aC).
+__device__ __forceinline__ void pair_line(const DevParams& P, double dx0, double dy0, double ddx, double ddy, double E,
+                                          double r0sq, double (&acc)[KC]) {
+    const double reach = fabs(dx0) + (KC - 1) * fabs(ddx);
+    if (reach < P.halfL - 1e-9) {
+        const double A = dx0 * dx0 + dy0 * dy0;
+        const double B = 2.0 * (dx0 * ddx + dy0 * ddy);
+        const double C = ddx * ddx + ddy * ddy;
+#pragma unroll
+        for (int a = 0; a < KC; ++a) {
+            const double r2 = fma((double)a, fma((double)a, C, B), A);
+            const double q2 = r0sq * fast_rcp(r2);
+            const double q6 = q2 * q2 * q2;
+            const double e = q6 * (q6 - 2.0);
+            acc[a] = (r2 > 0.0) ? fma(E, e, acc[a]) : acc[a];
+        }
+    } else {        // the pair straddles +-L/2 somewhere along the line: wrap every candidate (Periodic.py:8-20)
+#pragma unroll
+        for (int a = 0; a < KC; ++a) {
+            const double dx = put_in_box(fma((double)a, ddx, dx0), P.L, P.halfL);
+            const double dy = fma((double)a, ddy, dy0);
+            acc[a] += lj_energy(dx * dx + dy * dy, E, r0sq);
+        }
+    }
+}
+
+struct LineArgs {
+    DevParams P;
+    CellView ad;                 // base cell list of x (ad.sxy[slot] == x[ad.sidx[slot]])
+    CellView sub;
+    const double2* x;            // original order
+    const double2* s;            // original order
+    double scale;
+    double inv_step;             // 1/(20*scale): delta = s * inv_step (fast path only)
+    int n;
+    uint8_t* flag;               // [n] 1 = mover
+    int* movers;                 // [n] mover atom indices, ascending
+    int* n_movers;               // [1]
+    double* partial;             // [nblocks_energy][KC]
+    double* fix;                 // [n_movers][KC]
+    double* e_out;               // [KC]
+    int* amin_out;               // first argmin (ys.index(min(ys)))
+};
+
+// ---- phase M: movers ---------------------------------------------------------------------------
+__device__ __forceinline__ void line_mark_movers(const LineArgs& A, int gtid, int gthreads) {
+    for (int i = gtid; i < A.n; i += gthreads) {
+        const double2 p0 = A.x[i];
+        const double2 pe = cand2(p0, A.s[i], KC - 1, A.scale);
+        int nx0, ny0, nx1, ny1;
+        bin_index(A.P, p0.x, p0.y, nx0, ny0);
+        bin_index(A.P, pe.x, pe.y, nx1, ny1);
+        const bool in0 = nx0 >= 0 && nx0 < A.P.nbx && ny0 >= 0 && ny0 < A.P.nby;
+        A.flag[i] = (in0 && nx0 == nx1 && ny0 == ny1) ? 0 : 1;
+    }
+}
+
+// ---- phase C: ordered compaction of the flags (one block) ---------------------------------------
+__device__ __forceinline__ void line_compact_movers(const LineArgs& A, int* s_scan /* blockDim ints */) {
+    const int T = blockDim.x, t = threadIdx.x;
+    const int per = (A.n + T - 1) / T;
+    const int lo = t * per, hi = min(lo + per, A.n);
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += A.flag[i];
+    s_scan[t] = cnt;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {
+        int v = (t >= off) ? s_scan[t - off] : 0;
+        __syncthreads();
+        s_scan[t] += v;
+        __syncthreads();
+    }
+    int pos = s_scan[t] - cnt;
+    for (int i = lo; i < hi; ++i)
+        if (A.flag[i]) A.movers[pos++] = i;
+    if (t == T - 1) *A.n_movers = s_scan[t];
+    __syncthreads();
+}
+
+// ---- phase E: fast path over home cells ----------------------------------------------------------
+struct LineSmem {
+    double hx[LT_HOME], hy[LT_HOME], hsx[LT_HOME], hsy[LT_HOME];
+    int hslot[LT_HOME];                 // slot of the home atom, INT_MAX for movers (never paired here)
+    double tx[LT_TILE], ty[LT_TILE], tsx[LT_TILE], tsy[LT_TILE];
+    int tslot[LT_TILE];                 // same-cell partner: its slot (pair iff hslot < tslot); other cells: INT_MAX; movers: -1
+    double red[32];
+};
+
+// process the staged tile against the staged home atoms
+__device__ __forceinline__ void line_tile_pairs(const LineArgs& A, LineSmem& S, int nh, int nt, double E, double r0sq,
+                                                double (&acc)[KC]) {
+    const int total = nh * nt;
+    for (int p = threadIdx.x; p < total; p += blockDim.x) {
+        const int i = p % nh, j = p / nh;
+        if (S.hslot[i] >= S.tslot[j]) continue;
+        const double dx0 = put_in_box(S.tx[j] - S.hx[i], A.P.L, A.P.halfL);
+        const double dy0 = S.ty[j] - S.hy[i];
+        pair_line(A.P, dx0, dy0, S.tsx[j] - S.hsx[i], S.tsy[j] - S.hsy[i], E, r0sq, acc);
+    }
+}
+
+__device__ __forceinline__ void line_energy_cells(const LineArgs& A, LineSmem& S, int first_cell, int cell_stride,
+                                                  double (&acc)[KC]) {
+    const DevParams& P = A.P;
+    for (int c = first_cell; c < P.ncell; c += cell_stride) {
+        const int hb = A.ad.start[c], he = A.ad.start[c + 1];
+        if (hb == he) continue;
+        const int cx = c / P.nby, cy = c % P.nby;
+        // the stencil of an in-grid atom is a function of its cell: same code path as every other kernel
+        Stencil st;
+        {
+            int ys[3], xs[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                int vx = cx - 1 + i, vy = cy - 1 + i;
+                if (vx < 0) vx += P.nbx;
+                if (vx >= P.nbx) vx -= P.nbx;
+                if (vy < 0) vy += P.nby;
+                if (vy >= P.nby) vy -= P.nby;
+                xs[i] = vx; ys[i] = vy;
+            }
+            st.xs[0] = xs[0]; st.xs[1] = xs[1]; st.xs[2] = xs[2]; st.xs[3] = -1;
+            st.ys[0] = ys[0]; st.ys[1] = ys[1]; st.ys[2] = ys[2];
+            st.nxs = 3;
+            if (cx == 0) { st.xs[3] = P.nbx - 2; st.nxs = 4; }
+            else if (cx == P.nbx - 2) { st.xs[3] = 0; st.nxs = 4; }
+        }
+        for (int h0 = hb; h0 < he; h0 += LT_HOME) {
+            const int nh = min(LT_HOME, he - h0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+                const int slot = h0 + i, idx = A.ad.sidx[slot];
+                const double2 p = A.ad.sxy[slot], s = A.s[idx];
+                S.hx[i] = p.x; S.hy[i] = p.y;
+                S.hsx[i] = s.x * A.inv_step; S.hsy[i] = s.y * A.inv_step;
+                S.hslot[i] = A.flag[idx] ? 0x7fffffff : slot;
+            }
+            // ---- adatom partners (bins3x3 mode): cells c' >= c of the stencil, with multiplicity
+            if (P.aa_mode != 0) {
+                for (int a = 0; a < st.nxs; ++a) {
+                    const int nx = st.xs[a];
+                    if (nx < 0 || nx >= P.nbx) continue;
+                    for (int b = 0; b < 3; ++b) {
+                        const int ny = st.ys[b];
+                        if (ny < 0 || ny >= P.nby) continue;
+                        const int c2 = nx * P.nby + ny;
+                        if (c2 < c) continue;
+                        const int nb = A.ad.start[c2], ne = A.ad.start[c2 + 1];
+                        for (int t0 = nb; t0 < ne; t0 += LT_TILE) {
+                            const int nt = min(LT_TILE, ne - t0);
+                            __syncthreads();
+                            for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+                                const int slot = t0 + j, idx = A.ad.sidx[slot];
+                                const double2 p = A.ad.sxy[slot], s = A.s[idx];
+                                S.tx[j] = p.x; S.ty[j] = p.y;
+                                S.tsx[j] = s.x * A.inv_step; S.tsy[j] = s.y * A.inv_step;
+                                S.tslot[j] = A.flag[idx] ? -1 : (c2 == c ? slot : 0x7fffffff);
+                            }
+                            __syncthreads();
+                            line_tile_pairs(A, S, nh, nt, P.E_a, P.ra2, acc);
+                        }
+                    }
+                }
+            }
+            // ---- substrate partners: every cell of the stencil (static atoms: direction 0)
+            for (int a = 0; a < st.nxs; ++a) {
+                const int nx = st.xs[a];
+                if (nx < 0 || nx >= P.nbx) continue;
+                for (int b = 0; b < 3; ++b) {
+                    const int ny = st.ys[b];
+                    if (ny < 0 || ny >= P.nby) continue;
+                    const int c2 = nx * P.nby + ny;
+                    const int nb = A.sub.start[c2], ne = A.sub.start[c2 + 1];
+                    for (int t0 = nb; t0 < ne; t0 += LT_TILE) {
+                        const int nt = min(LT_TILE, ne - t0);
+                        __syncthreads();
+                        for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+                            const double2 p = A.sub.sxy[t0 + j];
+                            S.tx[j] = p.x; S.ty[j] = p.y; S.tsx[j] = 0.0; S.tsy[j] = 0.0;
+                            S.tslot[j] = 0x7ffffffe;       // pairs with every non-mover home atom... see below
+                        }
+                        __syncthreads();
+                        // movers carry hslot = INT_MAX > 0x7ffffffe, so they are skipped here as well
+                        line_tile_pairs(A, S, nh, nt, P.E_as, P.ras2, acc);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// all-pairs adatom sums (aa_mode 0, Energy.py:115-117): every pair i<j is always counted, only the
+// min-image wrap can change along the line (handled inside pair_line)
+__device__ __forceinline__ void line_energy_allpairs(const LineArgs& A, int gwarp, int nwarps, int lane, double (&acc)[KC]) {
+    for (int i = gwarp; i < A.n; i += nwarps) {
+        const double2 pi = A.x[i], si = A.s[i];
+        for (int j = i + 1 + lane; j < A.n; j += 32) {
+            const double2 pj = A.x[j], sj = A.s[j];
+            const double dx0 = put_in_box(pj.x - pi.x, A.P.L, A.P.halfL);
+            pair_line(A.P, dx0, pj.y - pi.y, (sj.x - si.x) * A.inv_step, (sj.y - si.y) * A.inv_step, A.P.E_a, A.P.ra2, acc);
+        }
+    }
+}
+
+// block-reduce the KC accumulators and store them as this block's partial
+__device__ __forceinline__ void line_store_partial(double (&acc)[KC], double* red, double* out) {
+#pragma unroll
+    for (int a = 0; a < KC; ++a) {
+        const double v = block_sum(acc[a], red);
+        if (threadIdx.x == 0) out[a] = v;
+    }
+}
+
+// ---- phase F: movers, one warp per (mover, candidate) ------------------------------------------
+__device__ __forceinline__ int stencil_multiplicity(const DevParams& P, const Stencil& st, int cx, int cy) {
+    int mx = 0, my = 0;
+    for (int a = 0; a < st.nxs; ++a) mx += (st.xs[a] == cx);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) my += (st.ys[b] == cy);
+    return mx * my;
+}
+
+__device__ __forceinline__ double line_fix_one(const LineArgs& A, int r, int a, int lane) {
+    const DevParams& P = A.P;
+    const int nm = *A.n_movers;
+    const int m = A.movers[r];
+    const double2 pm = cand2(A.x[m], A.s[m], a, A.scale);
+    int rx, ry;
+    bin_index(P, pm.x, pm.y, rx, ry);
+    const bool in_grid = rx >= 0 && rx < P.nbx && ry >= 0 && ry < P.nby;
+    const Stencil st = make_stencil(P, pm.x, pm.y);
+    double e = 0.0;
+    if (P.aa_mode != 0) {
+        // non-mover partners keep their base cell; an in-grid mover both sees them and is seen by them
+        // (symmetric stencil relation), an out-of-grid mover only sees partners with a higher index
+        visit_stencil(P, A.ad, st, lane, 32, [&](int slot) {
+            const int j = A.ad.sidx[slot];
+            if (A.flag[j] || (!in_grid && j < m)) return;
+            const double2 pj = cand2(A.x[j], A.s[j], a, A.scale);
+            e += pair_energy(P, pm.x, pm.y, pj, P.E_a, P.ra2);
+        });
+        // mover - mover: the lower index sees the higher one if the latter's cell is in its stencil
+        for (int r2 = r + 1 + lane; r2 < nm; r2 += 32) {
+            const int m2 = A.movers[r2];
+            const double2 p2 = cand2(A.x[m2], A.s[m2], a, A.scale);
+            int cx, cy;
+            bin_index(P, p2.x, p2.y, cx, cy);
+            if (cx < 0 || cx >= P.nbx || cy < 0 || cy >= P.nby) continue;
+            const int mult = stencil_multiplicity(P, st, cx, cy);
+            if (mult) e += mult * pair_energy(P, pm.x, pm.y, p2, P.E_a, P.ra2);
+        }
+    }
+    visit_stencil(P, A.sub, st, lane, 32, [&](int slot) { e += pair_energy(P, pm.x, pm.y, A.sub.sxy[slot], P.E_as, P.ras2); });
+    return group_sum<32>(e);
+}
+
+// ---- phase R: final sums + first argmin (one block of KC warps) ---------------------------------
+__device__ __forceinline__ void line_reduce(const LineArgs& A, int nblocks, double* s_e /* KC doubles */) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < KC) {
+        double v = 0.0;
+        for (int b = lane; b < nblocks; b += 32) v += A.partial[(size_t)b * KC + w];
+        const int nm = *A.n_movers;
+        for (int r = lane; r < nm; r += 32) v += A.fix[(size_t)r * KC + w];
+        v = group_sum<32>(v);
+        if (lane == 0) { s_e[w] = v; if (A.e_out) A.e_out[w] = v; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && A.amin_out) {
+        int am = 0;
+        double em = s_e[0];
+        for (int a = 1; a < KC; ++a)
+            if (s_e[a] < em) { em = s_e[a]; am = a; }
+        *A.amin_out = am;
+    }
+}
+
+// ================================================================================ standalone kernels
+__global__ void __launch_bounds__(256) k_line_mark(LineArgs A) {
+    line_mark_movers(A, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+__global__ void __launch_bounds__(1024) k_line_compact(LineArgs A) {
+    __shared__ int s_scan[1024];
+    line_compact_movers(A, s_scan);
+}
+
+__global__ void __launch_bounds__(LT_THREADS) k_line_energy(LineArgs A) {
+    __shared__ LineSmem S;
+    double acc[KC];
+#pragma unroll
+    for (int a = 0; a < KC; ++a) acc[a] = 0.0;
+    line_energy_cells(A, S, blockIdx.x, gridDim.x, acc);
+    if (A.P.aa_mode == 0) {
+        const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        line_energy_allpairs(A, gw, (gridDim.x * blockDim.x) >> 5, threadIdx.x & 31, acc);
+    }
+    __syncthreads();
+    line_store_partial(acc, S.red, A.partial + (size_t)blockIdx.x * KC);
+}
+
+__global__ void __launch_bounds__(128) k_line_fix(LineArgs A) {
+    const int nm = *A.n_movers;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int w = gw; w < nm * KC; w += nw) {
+        const double e = line_fix_one(A, w / KC, w % KC, lane);
+        if (lane == 0) A.fix[w] = e;
+    }
+}
+
+__global__ void __launch_bounds__(KC * 32) k_line_reduce(LineArgs A, int nblocks) {
+    __shared__ double s_e[KC];
+    line_reduce(A, nblocks, s_e);
+}
+
+}  // namespace kmc

@@ -257,6 +257,43 @@ def test_vs_oracle_sizes(W, Hs, Ha, n, aa):
         ctx.close()
 
 
+@pytest.mark.parametrize("W,Hs,Ha,n,aa,amp", [(18, 10, 10, 120, 0, 40.0), (18, 10, 10, 120, 1, 40.0), (48, 12, 10, 600, 1, 60.0),
+                                                (48, 12, 10, 600, 0, 5.0), (256, 256, 64, 10000, 1, 8.0),
+                                                (256, 256, 64, 10000, 1, 0.01)])
+def test_line_search_candidates_with_cell_crossings(W, Hs, Ha, n, aa, amp):
+    """The 20 candidates x + a*s/20/scale (2DGrowth.py:121,152) with directions large enough that many atoms
+    change cell, leave the grid or cross the +-L/2 seam along the line: every candidate energy must equal
+    RelaxEnergy of that candidate (per-candidate stencils, Energy.py:133-148 + Bins.py:44-84)."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(W, Hs, Ha, aa_mode=aa)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, n, seed=3 * W + n + aa)
+    rng = np.random.default_rng(W + n)
+    s = rng.normal(0.0, amp, ad.size)
+    s[1::2] = np.abs(s[1::2]) * 0.5          # keep atoms from diving into each other / the substrate
+    o = _oracle_for(gv)
+    osb = o.PutInBins(sub)
+    ctx = runtime.Context(runtime.params_from(gv), 0)
+    sb = ctx.bins_create(sub)
+    try:
+        for scale in (16, 64):
+            got = ctx.line_energies(ad, s, sb, scale, 20)
+            cands = [ad + a * s / 20 / scale for a in range(20)]
+            pick = range(20) if n <= 1000 else (0, 1, 7, 13, 19)
+            want = np.array([o.RelaxEnergy((cands[a], osb)) for a in pick])
+            assert relerr(got[list(pick)], want) < 1e-10, (scale, got[list(pick)], want)
+            # and the generic batched path agrees as well
+            gen = ctx.relax_energy(np.concatenate([cands[a] for a in pick]), sb, n=ad.size // 2, B=len(list(pick)))
+            assert relerr(gen, want) < 1e-10
+            # how many atoms actually changed cell: the test must exercise the mover path when amp is large
+            c0 = o.PutInBins(cands[0]).cell_of_atom()
+            c19 = o.PutInBins(cands[19]).cell_of_atom()
+            if amp >= 5.0 and scale == 16:
+                assert (c0 != c19).sum() > 0
+    finally:
+        sb.close()
+        ctx.close()
+
+
 def test_edge_cases():
     """empty / single-atom inputs and atoms outside the cell grid"""
     from kmcislandgrowth_b200 import Bins, Energy, Growth, Periodic, runtime
