@@ -21,10 +21,12 @@ struct DevParams {
 };
 
 // A cell list: atoms sorted by cell (column-major nx*nby+ny, input order kept inside a cell).
+// (no __restrict__: the persistent relaxation kernel rewrites these arrays between grid barriers, so
+// loads must stay on the coherent path)
 struct CellView {
-    const int* __restrict__ start;      // [ncell+2]
-    const double2* __restrict__ sxy;    // [n] cell-sorted positions
-    const int* __restrict__ sidx;       // [n] original index of every sorted slot
+    const int* start;      // [ncell+2]
+    const double2* sxy;    // [n] cell-sorted positions
+    const int* sidx;       // [n] original index of every sorted slot
     int n;
 };
 

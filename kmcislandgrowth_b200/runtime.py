@@ -327,6 +327,9 @@ class Context(object):
             check(rc)
         return st
 
+    def set_relax_mode(self, mode):
+        check(self.lib.kmc_set_relax_mode(self.handle, int(mode)))
+
     def deposit_place(self, sbins, u):
         check(self.lib.kmc_deposit_place(self.handle, sbins.handle, float(u)))
 
