@@ -161,8 +161,9 @@ int64_t kmc_state_count(KmcCtx* ctx);
 /* 2DGrowth.py:97-166 Relaxation(adatoms, substrate_bins, scale=16, threshold=1e-4) of the trajectory state:
  * 20-point line search + pseudo-CG + the reference's restart logic.  max_line_searches <= 0: no cap. */
 int kmc_relax(KmcCtx* ctx, const KmcBins* sbins, int32_t scale0, double threshold0, int64_t max_line_searches, KmcRelaxStats* stats);
-/* 1 (default): the relaxation runs as one persistent cooperative kernel; 0: host-driven loop of per-phase launches
- * (same arithmetic, kept as a cross-check).  Environment KMC_RELAX_MODE=host selects 0 at context creation. */
+/* 2 (default): the relaxation runs as one persistent cooperative kernel on cell-sorted state; 1: first-generation
+ * persistent kernel; 0: host-driven loop of per-phase launches (same arithmetic, kept as cross-checks).
+ * Environment KMC_RELAX_MODE=host|persistent1 selects 0|1 at context creation. */
 int kmc_set_relax_mode(KmcCtx* ctx, int mode);
 /* 2DGrowth.py:64-93 DepositAdatom placement (u = the uniform of :76), without the relaxation */
 int kmc_deposit_place(KmcCtx* ctx, const KmcBins* sbins, double u);

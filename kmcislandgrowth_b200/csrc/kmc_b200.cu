@@ -4,6 +4,7 @@
 #include "kmc_kernels.cuh"
 #include "kmc_line.cuh"
 #include "kmc_relax.cuh"
+#include "kmc_relax2.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -77,7 +78,8 @@ struct KmcCtx {
     // trajectory state
     double* st_xy = nullptr;
     int64_t st_n = 0, st_cap = 0;
-    int relax_mode = 1;             // 1: persistent cooperative kernel, 0: host-driven loop (cross-check)
+    int relax_mode = 2;             // 2: persistent kernel on cell-sorted state (default), 1: first-generation persistent kernel, 0: host-driven loop
+    size_t item_cap = 0;
     int sm_count = 148;
 };
 
@@ -85,7 +87,8 @@ enum Slot {
     S_IN0 = 0, S_IN1, S_IN2, S_IN3, S_OUT0, S_OUT1, S_OUT2, S_OUT3, S_OUT4, S_OUT5, S_OUT6, S_OUT7,
     S_CELLOF, S_START, S_CURSOR, S_SXY, S_SIDX, S_PARTIAL, S_DONE, S_CAND, S_E, S_CTRL,
     S_F, S_FAA, S_FAS, S_X0, S_XN, S_XNP, S_SN, S_TMP0, S_TMP1, S_TMP2, S_TMP3,
-    S_FLAG, S_MOVERS, S_NMOV, S_LPART, S_FIX, S_AMIN, S_RED, S_SYNC, S_COUNT
+    S_FLAG, S_MOVERS, S_NMOV, S_LPART, S_FIX, S_AMIN, S_RED, S_SYNC,
+    S_POS0, S_POS1, S_SD0, S_SD1, S_OI0, S_OI1, S_KEY, S_PERM, S_CHUNKS, S_ITEMS, S_COUNT
 };
 
 static int ensure(KmcCtx* c, DBuf& b, size_t bytes) {
@@ -393,7 +396,7 @@ int kmc_create(const KmcParams* p, int device, KmcCtx** out) {
     c->dp = to_dev(*p);
     c->slots.resize(S_COUNT);
     c->sm_count = sm_count;
-    if (const char* e = getenv("KMC_RELAX_MODE")) c->relax_mode = (strcmp(e, "host") == 0) ? 0 : 1;
+    if (const char* e = getenv("KMC_RELAX_MODE")) c->relax_mode = (strcmp(e, "host") == 0) ? 0 : (strcmp(e, "persistent1") == 0 ? 1 : 2);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(KMC_E_CUDA, "cudaStreamCreate failed"); }
     c->own_stream = true;
     if (cudaMallocHost(&c->h_mail, 4096) != cudaSuccess) { delete c; return fail(KMC_E_CUDA, "cudaMallocHost failed"); }
@@ -961,6 +964,96 @@ static int relax_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, double
     return 0;
 }
 
+// second-generation persistent kernel (kmc_relax2.cuh): cell-sorted state, balanced work items
+template <int G>
+static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
+    void* args[] = {(void*)&R};
+    c->launches++;
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    if (c->timing) { cudaEventCreate(&ea); cudaEventCreate(&eb); cudaEventRecord(ea, c->stream); }
+    CK(cudaLaunchCooperativeKernel((const void*)k_relax2<G>, dim3(blocks), dim3(R2_THREADS), args, 0, c->stream));
+    if (c->timing) { cudaEventRecord(eb, c->stream); c->recs.push_back({family_id(c, "relax_persistent"), ea, eb}); }
+    return 0;
+}
+
+static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, double threshold0, int64_t max_ls, KmcRelaxStats* stats) {
+    KmcRelaxStats st{};
+    const int n = (int)c->st_n;
+    if (n == 0) { if (stats) *stats = st; return 0; }
+    const int blocks = std::min(c->sm_count, std::max(1, (n + 15) / 16));
+    const int gthreads = blocks * R2_THREADS;
+    int G = 32;
+    while (G > 1 && (long long)n * G > gthreads) G >>= 1;
+    if (c->item_cap == 0) c->item_cap = (size_t)n * 4 + (size_t)c->dp.ncell * 2 + 1024;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        Relax2Args R{};
+        R.P = c->dp; R.sub = view_of(sb); R.n = n; R.ncell2 = c->dp.ncell + 2;
+        R.x0 = (double2*)c->st_xy;
+        TRY(slot(c, S_POS0, (size_t)n, &R.pos[0]));
+        TRY(slot(c, S_POS1, (size_t)n, &R.pos[1]));
+        TRY(slot(c, S_SD0, (size_t)n, &R.sdir[0]));
+        TRY(slot(c, S_SD1, (size_t)n, &R.sdir[1]));
+        TRY(slot(c, S_OI0, (size_t)n, &R.oidx[0]));
+        TRY(slot(c, S_OI1, (size_t)n, &R.oidx[1]));
+        TRY(slot(c, S_CELLOF, (size_t)n, &R.cellof));
+        TRY(slot(c, S_FLAG, (size_t)n, &R.flag));
+        TRY(slot(c, S_START, (size_t)R.ncell2, &R.start));
+        TRY(slot(c, S_CURSOR, (size_t)R.ncell2, &R.cursor));
+        TRY(slot(c, S_KEY, (size_t)n, &R.key));
+        TRY(slot(c, S_PERM, (size_t)n, &R.perm));
+        TRY(slot(c, S_CHUNKS, (size_t)c->dp.ncell * R2_PARTS + 2, &R.chunks));
+        TRY(slot(c, S_ITEMS, c->item_cap, &R.items));
+        R.item_cap = (int)c->item_cap;
+        TRY(slot(c, S_MOVERS, (size_t)n, &R.movers));
+        TRY(slot(c, S_LPART, (size_t)std::max(blocks, LINE_BLOCKS) * KC, &R.partial));
+        TRY(slot(c, S_FIX, (size_t)n * KC, &R.fix));
+        TRY(slot(c, S_RED, (size_t)blocks * 4, &R.red));
+        unsigned char* sync;
+        TRY(slot(c, S_SYNC, 256, &sync));
+        CK(cudaMemsetAsync(sync, 0, 256, c->stream));
+        R.barrier = (unsigned int*)sync;
+        R.need_rebuild = (int*)(sync + 16);
+        R.n_items = (int*)(sync + 20);
+        R.n_movers = (int*)(sync + 24);
+        R.pair_counter = (unsigned long long*)(sync + 32);
+        R.stats = (KmcRelaxStatsDev*)(sync + 64);
+        R.phase_ns = (unsigned long long*)(sync + 128);
+        R.scale0 = scale0; R.threshold0 = threshold0; R.max_ls = max_ls;
+        switch (G) {
+            case 32: TRY(launch_relax2<32>(c, R, blocks)); break;
+            case 16: TRY(launch_relax2<16>(c, R, blocks)); break;
+            case 8: TRY(launch_relax2<8>(c, R, blocks)); break;
+            case 4: TRY(launch_relax2<4>(c, R, blocks)); break;
+            case 2: TRY(launch_relax2<2>(c, R, blocks)); break;
+            default: TRY(launch_relax2<1>(c, R, blocks)); break;
+        }
+        TRY(mail(c, sync, 256));
+        const char* hm = (const char*)c->h_mail;
+        const KmcRelaxStatsDev* ds = (const KmcRelaxStatsDev*)(hm + 64);
+        if (ds->status == -4) {            // work list overflow: grow and run again (x0 is untouched)
+            const int need = *(const int*)(hm + 20);
+            c->item_cap = (size_t)need + need / 2 + 1024;
+            continue;
+        }
+        const unsigned long long visits = *(const unsigned long long*)(hm + 32);
+        if (getenv("KMC_PHASE_TIMING")) {
+            const unsigned long long* ph = (const unsigned long long*)(hm + 128);
+            const double nls = ds->line_searches > 0 ? (double)ds->line_searches : 1.0;
+            fprintf(stderr, "[kmc2 phase us/ls] E %.2f | bar %.2f | fix+bar %.2f | S %.2f | bar %.2f | G %.2f | bar %.2f  (ls=%lld blocks=%d G=%d items=%d)\n",
+                    ph[0] / nls * 1e-3, ph[1] / nls * 1e-3, ph[2] / nls * 1e-3, ph[3] / nls * 1e-3, ph[4] / nls * 1e-3, ph[5] / nls * 1e-3,
+                    ph[6] / nls * 1e-3, (long long)ds->line_searches, blocks, G, *(const int*)(hm + 20));
+        }
+        st.line_searches = ds->line_searches; st.restarts = ds->restarts; st.maxF = ds->maxF;
+        st.final_threshold = ds->final_threshold; st.final_scale = ds->final_scale; st.status = ds->status;
+        const long long per_sweep = (long long)visits + (c->dp.aa_mode == 0 ? (long long)n * (n - 1) / 2 : 0);
+        st.pair_evals = st.line_searches * KC * per_sweep;
+        if (stats) *stats = st;
+        if (st.status != 0) return fail(st.status, "relaxation stopped at the line-search cap (%lld)", (long long)max_ls);
+        return 0;
+    }
+    return fail(KMC_E_CAPACITY, "relaxation work list kept overflowing");
+}
+
 extern "C" {
 
 int kmc_relax(KmcCtx* c, const KmcBins* sb, int32_t scale0, double threshold0, int64_t max_ls, KmcRelaxStats* stats) {
@@ -968,11 +1061,12 @@ int kmc_relax(KmcCtx* c, const KmcBins* sb, int32_t scale0, double threshold0, i
     if (scale0 < 1 || !(threshold0 > 0)) return fail(KMC_E_ARG, "bad scale0 / threshold0");
     TRY(state_reserve(c, c->st_n + 1));
     if (c->relax_mode == 0) return relax_host_driven(c, sb, scale0, threshold0, max_ls, stats);
+    if (c->relax_mode == 2) return relax2_persistent(c, sb, scale0, threshold0, max_ls, stats);
     return relax_persistent(c, sb, scale0, threshold0, max_ls, stats);
 }
 
 int kmc_set_relax_mode(KmcCtx* c, int mode) {
-    if (!c || (mode != 0 && mode != 1)) return fail(KMC_E_ARG, "relax mode must be 0 (host-driven) or 1 (persistent kernel)");
+    if (!c || mode < 0 || mode > 2) return fail(KMC_E_ARG, "relax mode must be 0 (host-driven), 1 (persistent kernel v1) or 2 (persistent kernel on sorted state)");
     c->relax_mode = mode;
     return 0;
 }

@@ -1,0 +1,595 @@
+// kmc_relax2.cuh -- Relaxation (2DGrowth.py:97-166) as one persistent cooperative kernel, second
+// generation: the trajectory lives in CELL-SORTED order for the whole relaxation (positions,
+// directions, original indices), so every pass is coalesced and free of gathers; the line-search
+// energy is split into equal-sized work items (<= 64 pairs) that are dealt to warps statically,
+// which balances the grid and keeps every sum in a fixed order (bit-reproducible runs); the CG
+// update and the mover flags of the next line are fused into the force phase, leaving three grid
+// barriers per line search:
+//
+//   E: line-search energy over the work items (+ ordered mover list by block 0)            ||
+//      [F: mover fix-up, only when movers exist                                            ||]
+//   S: candidate sums, first argmin, x_np = candidate, top/bot/min-y partials, cell check   ||
+//      [rebuild of the sorted state when a mover really changed cell at the winner]
+//   G: forces at x_np, max|F|^2 partials, s <- F + beta s, mover flags of the next line    ||
+//   C: control (every block, identical arithmetic): converged / stalled / out of bounds / continue
+#pragma once
+#include "kmc_line.cuh"
+#include "kmc_relax.cuh"
+
+namespace kmc {
+
+constexpr int R2_THREADS = 512;
+constexpr int R2_CHUNK = 64;        // pairs per work item
+constexpr int R2_PARTS = 8;         // per home cell: adatom columns 0..3, substrate columns 0..3
+
+struct WorkItem {
+    int cell;      // home cell
+    int part;      // 0..3 adatom partner column, 4..7 substrate partner column
+    int begin;     // first pair of the chunk in the (home x partner) pair space
+    int count;     // pairs in the chunk
+};
+
+struct Relax2Args {
+    DevParams P;
+    CellView sub;
+    int n, ncell2;
+    double2* x0;            // original order: input and output of the relaxation
+    double2* pos[2];        // sorted: base iterate / candidate winner (ping-pong)
+    double2* sdir[2];       // sorted: search direction (ping-pong across rebuilds)
+    int* oidx[2];           // sorted: original index
+    int* cellof;            // sorted: cell of the slot in the current cell list
+    uint8_t* flag;          // sorted: 1 = mover on the current line
+    int* start;             // [ncell+2]
+    int* cursor;            // [ncell+2]
+    int* key;               // [n] scratch: cell of source element
+    int* perm;              // [n] scratch: source element of a slot
+    int* chunks;            // [ncell*R2_PARTS + 1] items per (cell, part), then their exclusive scan
+    WorkItem* items;        // work list
+    int* n_items;
+    int item_cap;
+    int* movers;            // slots of the movers, ascending
+    int* n_movers;
+    double* partial;        // [KC][gridDim] candidate partial sums (transposed: coalesced reads)
+    double* fix;            // [n][KC]
+    double* red;            // [gridDim][4] top, bot, miny, maxF
+    unsigned int* barrier;
+    int* need_rebuild;
+    unsigned long long* pair_counter;
+    int scale0;
+    double threshold0;
+    long long max_ls;
+    KmcRelaxStatsDev* stats;
+    unsigned long long* phase_ns;
+};
+
+struct Relax2Smem {
+    int scan[R2_THREADS];
+    double wred[R2_THREADS / 32][KC];
+    double e[KC];
+    double ctl[4];
+    double red[32];
+};
+
+// stencil of an in-grid cell (same rule as make_stencil, driven by cell coordinates)
+__device__ __forceinline__ Stencil cell_stencil(const DevParams& P, int cx, int cy) {
+    Stencil st;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int vx = cx - 1 + i, vy = cy - 1 + i;
+        if (vx < 0) vx += P.nbx;
+        if (vx >= P.nbx) vx -= P.nbx;
+        if (vy < 0) vy += P.nby;
+        if (vy >= P.nby) vy -= P.nby;
+        st.xs[i] = vx;
+        st.ys[i] = vy;
+    }
+    st.nxs = 3;
+    st.xs[3] = -1;
+    if (cx == 0) { st.xs[3] = P.nbx - 2; st.nxs = 4; }
+    else if (cx == P.nbx - 2) { st.xs[3] = 0; st.nxs = 4; }
+    return st;
+}
+
+// partner ranges of (home cell c, part): up to three (begin, end) slot ranges, in stencil order.
+// Adatom parts keep only cells c2 >= c (every unordered pair once, with the stencil's multiplicity).
+struct Ranges {
+    int b[3], e[3];
+    int self[3];      // 1 when the range is the home cell itself (pair only if slot_i < slot_j)
+    int total;
+};
+__device__ __forceinline__ Ranges partner_ranges(const DevParams& P, const int* ad_start, const int* sub_start, int c, int part) {
+    Ranges r;
+    r.total = 0;
+    const int cx = c / P.nby, cy = c % P.nby;
+    const Stencil st = cell_stencil(P, cx, cy);
+    const int a = part & 3;
+    const bool is_sub = part >= 4;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r.b[k] = r.e[k] = 0; r.self[k] = 0; }
+    if (a >= st.nxs) return r;
+    const int nx = st.xs[a];
+    if (nx < 0 || nx >= P.nbx) return r;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int ny = st.ys[k];
+        if (ny < 0 || ny >= P.nby) continue;
+        const int c2 = nx * P.nby + ny;
+        if (!is_sub && c2 < c) continue;
+        const int* s = is_sub ? sub_start : ad_start;
+        r.b[k] = s[c2];
+        r.e[k] = s[c2 + 1];
+        r.self[k] = (!is_sub && c2 == c) ? 1 : 0;
+        r.total += r.e[k] - r.b[k];
+    }
+    return r;
+}
+
+// ---- rebuild of the sorted state from `n` source elements (7 barriers) ---------------------------
+// src_s / src_oidx may be null (direction 0 / identity index).
+__device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double2* src_pos, const double2* src_s, const int* src_oidx,
+                                               double2* dst_pos, double2* dst_s, int* dst_oidx, unsigned int& epoch, Relax2Smem& S) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const DevParams& P = R.P;
+    for (int c = gtid; c < R.ncell2; c += gthreads) R.start[c] = 0;
+    grid_barrier(R.barrier, epoch);
+    for (int k = gtid; k < R.n; k += gthreads) {
+        int nx, ny;
+        bin_index(P, src_pos[k].x, src_pos[k].y, nx, ny);
+        const int c = flat_cell(P, nx, ny);
+        R.key[k] = c;
+        atomicAdd(&R.start[1 + c], 1);
+    }
+    grid_barrier(R.barrier, epoch);
+    if (blockIdx.x == 0) {
+        const int T = blockDim.x, t = threadIdx.x;
+        const int m = R.ncell2 - 1;
+        const int per = (m + T - 1) / T;
+        const int lo = 1 + t * per, hi = min(lo + per, R.ncell2);
+        int sum = 0;
+        for (int i = lo; i < hi; ++i) sum += R.start[i];
+        S.scan[t] = sum;
+        __syncthreads();
+        for (int off = 1; off < T; off <<= 1) {
+            int v = (t >= off) ? S.scan[t - off] : 0;
+            __syncthreads();
+            S.scan[t] += v;
+            __syncthreads();
+        }
+        int run = S.scan[t] - sum;
+        for (int i = lo; i < hi; ++i) { run += R.start[i]; R.start[i] = run; }
+        __syncthreads();
+        for (int i = t; i < R.ncell2; i += T) R.cursor[i] = R.start[i];
+    }
+    grid_barrier(R.barrier, epoch);
+    for (int k = gtid; k < R.n; k += gthreads) {
+        const int slot = atomicAdd(&R.cursor[R.key[k]], 1);
+        R.perm[slot] = k;
+    }
+    grid_barrier(R.barrier, epoch);
+    // per cell: order by original index (deterministic), move the payload, count the work items
+    for (int c = gtid; c < R.ncell2 - 1; c += gthreads) {
+        const int lo = R.start[c], hi = R.start[c + 1];
+        for (int i = lo + 1; i < hi; ++i) {          // insertion sort of perm[lo..hi) keyed on the original index
+            const int v = R.perm[i];
+            const int kv = src_oidx ? src_oidx[v] : v;
+            int j = i - 1;
+            while (j >= lo) {
+                const int w = R.perm[j];
+                if ((src_oidx ? src_oidx[w] : w) <= kv) break;
+                R.perm[j + 1] = w;
+                --j;
+            }
+            R.perm[j + 1] = v;
+        }
+        for (int s = lo; s < hi; ++s) {
+            const int k = R.perm[s];
+            dst_pos[s] = src_pos[k];
+            dst_s[s] = src_s ? src_s[k] : make_double2(0.0, 0.0);
+            dst_oidx[s] = src_oidx ? src_oidx[k] : k;
+            R.cellof[s] = c;
+        }
+        if (c < P.ncell) {
+            const int nh = hi - lo;
+#pragma unroll
+            for (int part = 0; part < R2_PARTS; ++part) {
+                int cnt = 0;
+                if (nh > 0 && !(part < 4 && P.aa_mode == 0)) {
+                    const Ranges r = partner_ranges(P, R.start, R.sub.start, c, part);
+                    cnt = (nh * r.total + R2_CHUNK - 1) / R2_CHUNK;
+                }
+                R.chunks[1 + c * R2_PARTS + part] = cnt;
+            }
+        }
+    }
+    if (gtid == 0) R.chunks[0] = 0;
+    grid_barrier(R.barrier, epoch);
+    if (blockIdx.x == 0) {      // inclusive scan of chunks[1..ncell*PARTS]
+        const int T = blockDim.x, t = threadIdx.x;
+        const int m = P.ncell * R2_PARTS;
+        const int per = (m + T - 1) / T;
+        const int lo = 1 + t * per, hi = min(lo + per, m + 1);
+        int sum = 0;
+        for (int i = lo; i < hi; ++i) sum += R.chunks[i];
+        S.scan[t] = sum;
+        __syncthreads();
+        for (int off = 1; off < T; off <<= 1) {
+            int v = (t >= off) ? S.scan[t - off] : 0;
+            __syncthreads();
+            S.scan[t] += v;
+            __syncthreads();
+        }
+        int run = S.scan[t] - sum;
+        for (int i = lo; i < hi; ++i) { run += R.chunks[i]; R.chunks[i] = run; }
+        if (t == T - 1) *R.n_items = S.scan[t];      // true total; the caller checks it against item_cap
+    }
+    grid_barrier(R.barrier, epoch);
+    for (int q = gtid; q < P.ncell * R2_PARTS; q += gthreads) {
+        const int first = R.chunks[q], last = R.chunks[q + 1];
+        if (first == last) continue;
+        const int c = q / R2_PARTS, part = q % R2_PARTS;
+        const int nh = R.start[c + 1] - R.start[c];
+        const Ranges r = partner_ranges(P, R.start, R.sub.start, c, part);
+        const int pairs = nh * r.total;
+        for (int k = first; k < last && k < R.item_cap; ++k) {
+            WorkItem it;
+            it.cell = c; it.part = part; it.begin = (k - first) * R2_CHUNK;
+            it.count = min(R2_CHUNK, pairs - it.begin);
+            R.items[k] = it;
+        }
+    }
+    grid_barrier(R.barrier, epoch);
+}
+
+// ---- E: one work item, 32 lanes -----------------------------------------------------------------
+__device__ __forceinline__ void relax2_item(const Relax2Args& R, const WorkItem it, const double2* pos, const double2* sdir,
+                                            double inv_step, int lane, double (&acc)[KC]) {
+    const DevParams& P = R.P;
+    const int hb = R.start[it.cell], nh = R.start[it.cell + 1] - hb;
+    const Ranges r = partner_ranges(P, R.start, R.sub.start, it.cell, it.part);
+    const bool is_sub = it.part >= 4;
+    const int n0 = r.e[0] - r.b[0], n1 = r.e[1] - r.b[1];
+    for (int q = it.begin + lane; q < it.begin + it.count; q += 32) {
+        const int i = q % nh, j = q / nh;
+        const int hs = hb + i;
+        int js, self;
+        if (j < n0) { js = r.b[0] + j; self = r.self[0]; }
+        else if (j < n0 + n1) { js = r.b[1] + (j - n0); self = r.self[1]; }
+        else { js = r.b[2] + (j - n0 - n1); self = r.self[2]; }
+        if (R.flag[hs]) continue;                               // movers are handled by the fix-up phase
+        const double2 pi = pos[hs], si = sdir[hs];
+        if (is_sub) {
+            const double2 pj = R.sub.sxy[js];
+            const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
+            pair_line(P, dx0, pj.y - pi.y, -si.x * inv_step, -si.y * inv_step, P.E_as, P.ras2, acc);
+        } else {
+            if (R.flag[js] || (self && js <= hs)) continue;
+            const double2 pj = pos[js], sj = sdir[js];
+            const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
+            pair_line(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, acc);
+        }
+    }
+}
+
+// ---- F: one (mover, candidate) by one warp; sorted-state version of line_fix_one ------------------
+__device__ __forceinline__ double relax2_fix_one(const Relax2Args& R, const double2* pos, const double2* sdir, const int* oidx,
+                                                 double scale, int r, int a, int lane) {
+    const DevParams& P = R.P;
+    const int nm = *R.n_movers;
+    const int m = R.movers[r];
+    const int om = oidx[m];
+    const double2 pm = cand2(pos[m], sdir[m], a, scale);
+    int rx, ry;
+    bin_index(P, pm.x, pm.y, rx, ry);
+    const bool in_grid = rx >= 0 && rx < P.nbx && ry >= 0 && ry < P.nby;
+    const Stencil st = make_stencil(P, pm.x, pm.y);
+    CellView ad;
+    ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = R.n;
+    double e = 0.0;
+    if (P.aa_mode != 0) {
+        visit_stencil(P, ad, st, lane, 32, [&](int slot) {
+            if (R.flag[slot] || (!in_grid && oidx[slot] < om)) return;
+            const double2 pj = cand2(pos[slot], sdir[slot], a, scale);
+            e += pair_energy(P, pm.x, pm.y, pj, P.E_a, P.ra2);
+        });
+        for (int r2 = lane; r2 < nm; r2 += 32) {               // mover - mover: the lower index sees the higher one
+            const int m2 = R.movers[r2];
+            if (oidx[m2] <= om) continue;
+            const double2 p2 = cand2(pos[m2], sdir[m2], a, scale);
+            int cx, cy;
+            bin_index(P, p2.x, p2.y, cx, cy);
+            if (cx < 0 || cx >= P.nbx || cy < 0 || cy >= P.nby) continue;
+            const int mult = stencil_multiplicity(P, st, cx, cy);
+            if (mult) e += mult * pair_energy(P, pm.x, pm.y, p2, P.E_a, P.ra2);
+        }
+    }
+    visit_stencil(P, R.sub, st, lane, 32, [&](int slot) { e += pair_energy(P, pm.x, pm.y, R.sub.sxy[slot], P.E_as, P.ras2); });
+    return group_sum<32>(e);
+}
+
+__device__ __forceinline__ uint8_t mover_flag(const DevParams& P, double2 p0, double2 s, double scale) {
+    const double2 pe = cand2(p0, s, KC - 1, scale);
+    int nx0, ny0, nx1, ny1;
+    bin_index(P, p0.x, p0.y, nx0, ny0);
+    bin_index(P, pe.x, pe.y, nx1, ny1);
+    const bool in0 = nx0 >= 0 && nx0 < P.nbx && ny0 >= 0 && ny0 < P.nby;
+    return (in0 && nx0 == nx1 && ny0 == ny1) ? 0 : 1;
+}
+
+// ---- G: forces at `pos` (+ optional fused CG update / mover flags) --------------------------------
+// mode 0: sdir <- F (the first direction dx0, 2DGrowth.py:120,125), count pairs when asked
+// mode 1: max|F|^2 partial, sdir <- F + beta*sdir (2DGrowth.py:147), flag <- mover test of the next line
+template <int G>
+__device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2* pos, double2* sdir, const int* oidx, int mode, double beta,
+                                              double scale, bool count_pairs, Relax2Smem& S) {
+    const DevParams& P = R.P;
+    const int lane = threadIdx.x & (G - 1);
+    const int ggroups = (gridDim.x * blockDim.x) / G;
+    const int rounds = (R.n + ggroups - 1) / ggroups;
+    CellView ad;
+    ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = R.n;
+    double mf = 0.0;
+    unsigned long long visits = 0;
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int slot = rd * ggroups + (blockIdx.x * blockDim.x + threadIdx.x) / G;
+        const bool live = slot < R.n;
+        double ax = 0, ay = 0, sx = 0, sy = 0;
+        double2 pi = make_double2(0, 0);
+        if (live) {
+            pi = pos[slot];
+            const Stencil st = make_stencil(P, pi.x, pi.y);
+            if (P.aa_mode == 0) {
+                for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
+            } else {
+                visit_stencil(P, ad, st, lane, G, [&](int s) {
+                    acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
+                    ++visits;
+                });
+            }
+            visit_stencil(P, R.sub, st, lane, G, [&](int s) {
+                acc_force(P, pi.x, pi.y, R.sub.sxy[s], P.E_as, P.ras2, sx, sy);
+                ++visits;
+            });
+        }
+        ax = group_sum<G>(ax); ay = group_sum<G>(ay);
+        sx = group_sum<G>(sx); sy = group_sum<G>(sy);
+        if (live && lane == 0) {
+            const double fx = ax + sx, fy = ay + sy;                // 2DGrowth.py:120
+            double2 sn;
+            if (mode == 0) {
+                sn = make_double2(fx, fy);
+            } else {
+                mf = fmax(mf, fx * fx + fy * fy);                   // :129,160
+                const double2 so = sdir[slot];
+                sn = make_double2(__dadd_rn(fx, __dmul_rn(beta, so.x)), __dadd_rn(fy, __dmul_rn(beta, so.y)));   // :147
+            }
+            sdir[slot] = sn;
+            R.flag[slot] = mover_flag(P, pi, sn, scale);
+        }
+    }
+    if (mode == 1) {
+        const double r_mf = block_max(mf, S.red);
+        if (threadIdx.x == 0) R.red[(size_t)blockIdx.x * 4 + 3] = r_mf;
+    }
+    if (count_pairs) {
+        for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
+        if ((threadIdx.x & 31) == 0 && visits) atomicAdd(R.pair_counter, visits);
+    }
+}
+
+#define PHASE2_MARK(k)                                             \
+    if (gtid == 0) {                                               \
+        const unsigned long long _t = gtimer();                    \
+        R.phase_ns[k] += _t - t_mark;                              \
+        t_mark = _t;                                               \
+    }
+
+template <int G>
+__global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
+    __shared__ Relax2Smem S;
+    unsigned int epoch = 0;
+    const DevParams& P = R.P;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gwarp = gtid >> 5, nwarps = gthreads >> 5;
+    const int nblk = gridDim.x;
+
+    int cur = 0;          // pos[cur] = base iterate x_n, pos[cur^1] = x_np
+    int cs = 0;           // sdir[cs], oidx[cs] current
+    int scale = R.scale0;
+    double threshold = R.threshold0;
+    long long ls = 0, restarts = 0;
+    int status = 0;
+    double maxF = 0.0, lastmaxF = 0.0;
+    bool first_pass = true;
+    bool overflow = false;
+    unsigned long long t_mark = gtimer();
+
+    // candidate sums, argmin, x_np, partial reductions; returns after the barrier that publishes x_np
+    auto line_search = [&]() {
+        const double dscale = (double)scale;
+        const double inv_step = 1.0 / (20.0 * dscale);
+        const double2* pos = R.pos[cur];
+        double2* posn = R.pos[cur ^ 1];
+        double2* sdir = R.sdir[cs];
+        const int* oidx = R.oidx[cs];
+        // ---------------- E
+        if (blockIdx.x == 0) {          // ordered list of mover slots
+            const int T = blockDim.x, t = threadIdx.x;
+            const int per = (R.n + T - 1) / T;
+            const int lo = t * per, hi = min(lo + per, R.n);
+            int cnt = 0;
+            for (int i = lo; i < hi; ++i) cnt += R.flag[i];
+            S.scan[t] = cnt;
+            __syncthreads();
+            for (int off = 1; off < T; off <<= 1) {
+                int v = (t >= off) ? S.scan[t - off] : 0;
+                __syncthreads();
+                S.scan[t] += v;
+                __syncthreads();
+            }
+            int p = S.scan[t] - cnt;
+            for (int i = lo; i < hi; ++i)
+                if (R.flag[i]) R.movers[p++] = i;
+            if (t == T - 1) *R.n_movers = S.scan[t];
+        }
+        double acc[KC];
+#pragma unroll
+        for (int a = 0; a < KC; ++a) acc[a] = 0.0;
+        const int n_items = *R.n_items;
+        for (int k = gwarp; k < n_items; k += nwarps) relax2_item(R, R.items[k], pos, sdir, inv_step, lane, acc);
+        if (P.aa_mode == 0) {
+            for (int i = gwarp; i < R.n; i += nwarps) {
+                const double2 pi = pos[i], si = sdir[i];
+                for (int j = i + 1 + lane; j < R.n; j += 32) {
+                    const double2 pj = pos[j], sj = sdir[j];
+                    const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
+                    pair_line(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, acc);
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < KC; ++a) {
+            const double v = group_sum<32>(acc[a]);
+            if (lane == 0) S.wred[warp][a] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < KC) {
+            double v = 0.0;
+            for (int w = 0; w < R2_THREADS / 32; ++w) v += S.wred[w][threadIdx.x];
+            R.partial[(size_t)threadIdx.x * nblk + blockIdx.x] = v;
+        }
+        PHASE2_MARK(0)
+        grid_barrier(R.barrier, epoch);
+        PHASE2_MARK(1)
+        // ---------------- F
+        const int nm = *R.n_movers;
+        if (nm > 0) {
+            for (int w = gwarp; w < nm * KC; w += nwarps) {
+                const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane);
+                if (lane == 0) R.fix[w] = e;
+            }
+            grid_barrier(R.barrier, epoch);
+            PHASE2_MARK(2)
+        }
+        // ---------------- S
+        for (int a = warp; a < KC; a += R2_THREADS / 32) {
+            double v = 0.0;
+            for (int b = lane; b < nblk; b += 32) v += R.partial[(size_t)a * nblk + b];
+            for (int r = lane; r < nm; r += 32) v += R.fix[(size_t)r * KC + a];
+            v = group_sum<32>(v);
+            if (lane == 0) S.e[a] = v;
+        }
+        __syncthreads();
+        int amin = 0;
+        {
+            double em = S.e[0];
+            for (int a = 1; a < KC; ++a)
+                if (S.e[a] < em) { em = S.e[a]; amin = a; }                // first argmin, 2DGrowth.py:123,155
+        }
+        double top = 0.0, bot = 0.0, my = INFINITY;
+        for (int slot = gtid; slot < R.n; slot += gthreads) {
+            const double2 p0 = pos[slot];
+            const double2 p = cand2(p0, sdir[slot], amin, dscale);
+            posn[slot] = p;
+            top += p.x * (p.x - p0.x) + p.y * (p.y - p0.y);                // :143
+            bot += p0.x * p0.x + p0.y * p0.y;                              // :144
+            my = fmin(my, p.y);                                            // :137
+            if (R.flag[slot]) {
+                int nx, ny;
+                bin_index(P, p.x, p.y, nx, ny);
+                if (flat_cell(P, nx, ny) != R.cellof[slot]) *R.need_rebuild = 1;
+            }
+        }
+        {
+            const double r_top = block_sum(top, S.red);
+            const double r_bot = block_sum(bot, S.red);
+            const double r_my = block_min(my, S.red);
+            if (threadIdx.x == 0) {
+                double* o = R.red + (size_t)blockIdx.x * 4;
+                o[0] = r_top; o[1] = r_bot; o[2] = r_my;
+            }
+        }
+        PHASE2_MARK(3)
+        grid_barrier(R.barrier, epoch);
+        PHASE2_MARK(4)
+        // every block: beta and min-y from the same partials in the same order
+        if (threadIdx.x < 32) {
+            double t2 = 0.0, b2 = 0.0, m2 = INFINITY;
+            for (int b = lane; b < nblk; b += 32) {
+                const double* o = R.red + (size_t)b * 4;
+                t2 += o[0]; b2 += o[1]; m2 = fmin(m2, o[2]);
+            }
+            t2 = group_sum<32>(t2); b2 = group_sum<32>(b2); m2 = group_min<32>(m2);
+            if (lane == 0) { S.ctl[0] = t2; S.ctl[1] = b2; S.ctl[2] = m2; }
+        }
+        __syncthreads();
+        const double beta = S.ctl[0] / S.ctl[1];                          // :143-145
+        // ---------------- rebuild (rare) + G
+        if (*R.need_rebuild) {
+            relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S);
+            if (gtid == 0) *R.need_rebuild = 0;
+            if (*R.n_items > R.item_cap) overflow = true;
+            cs ^= 1;          // the rebuilt x_np now lives in pos[cur]: make it the "next" buffer by flipping cur
+            cur ^= 1;
+        }
+        relax2_forces<G>(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S);
+        PHASE2_MARK(5)
+        grid_barrier(R.barrier, epoch);
+        PHASE2_MARK(6)
+        if (threadIdx.x < 32) {
+            double mf = 0.0;
+            for (int b = lane; b < nblk; b += 32) mf = fmax(mf, R.red[(size_t)b * 4 + 3]);
+            for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+            if (lane == 0) S.ctl[3] = mf;
+        }
+        __syncthreads();
+        ++ls;
+    };
+
+    for (;;) {                                                         // one pass == one (recursive) call of Relaxation
+        if (scale > 1024) { scale = 16; threshold *= 10; }              // :111-113
+        relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S);
+        if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
+        relax2_forces<G>(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S);   // dx0, sn = dx0  :120,125
+        first_pass = false;
+        grid_barrier(R.barrier, epoch);
+        line_search();                                                  // :121-129
+        if (overflow) { status = -4; break; }
+        maxF = S.ctl[3];
+        lastmaxF = maxF;
+        bool restart = false;
+        while (maxF > threshold) {                                      // :131
+            if (R.max_ls > 0 && ls >= R.max_ls) { status = -6; break; }
+            if (S.ctl[2] > P.Dmax) { restart = true; break; }           // :137-140
+            cur ^= 1;                                                   // x_n <- x_np ; s_n already updated in phase G  (:147-150)
+            line_search();                                              // :152-160
+            if (overflow) { status = -4; break; }
+            maxF = S.ctl[3];
+            if (fabs(lastmaxF - maxF) < 1e-8) { restart = true; break; }    // :162-164
+            lastmaxF = maxF;
+        }
+        if (status != 0 || !restart) break;
+        ++restarts;
+        scale *= 2;
+    }
+    // result: PutAllInBox(x_np) in the original order   (:166)
+    if (status != -4) {
+        const double2* posn = R.pos[cur ^ 1];
+        const int* oidx = R.oidx[cs];
+        for (int slot = gtid; slot < R.n; slot += gthreads) {
+            double2 p = posn[slot];
+            p.x = put_in_box(p.x, P.L, P.halfL);
+            R.x0[oidx[slot]] = p;
+        }
+    }
+    if (gtid == 0) {
+        R.stats->line_searches = ls;
+        R.stats->restarts = restarts;
+        R.stats->maxF = maxF;
+        R.stats->final_threshold = threshold;
+        R.stats->final_scale = scale;
+        R.stats->status = status;
+    }
+}
+
+}  // namespace kmc
