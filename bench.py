@@ -57,15 +57,16 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag.is_set():
                     break
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t_begin=0.0, t_end=float("inf")):
+        """summary of the samples taken inside [t_begin, t_end] (the timed region)"""
         self.stop_flag.set()
         if self.proc is not None:
             try:
@@ -73,7 +74,9 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for (ts, r) in self.rows:
+            if ts < t_begin or ts > t_end:
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -212,6 +215,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     # untimed set-up: bring the synthetic film to a relaxed state (bounded)
     st = ctx.relax(sim.sbins, 16, 1e-4, args.prerelax)
     nsteps = args.warmup + args.steps
@@ -220,33 +225,33 @@ def run_ours(args):
         sim.step(us[s, 0], us[s, 1], cap)
 
     # ---- timed region 1: device-resident trajectory
-    sampler = ClockSampler(local)
-    sampler.start()
+    state0 = sim.adatoms.copy()           # both timed regions run the SAME events from this state
     ctx.timing_reset()
     ctx.timing(True)
     l0 = ctx.launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    t_begin1 = t0
     e0.record()
     recs = []
     for s in range(args.steps):
         recs.append(sim.step(us[args.warmup + s, 0], us[args.warmup + s, 1], cap))
     e1.record()
     barrier()
-    wall_dev = time.perf_counter() - t0
+    t_end = time.perf_counter()
+    wall_dev = t_end - t0
     t_dev = e0.elapsed_time(e1) * 1e-3        # CUDA events on the launching stream
     launches = ctx.launch_count() - l0
     ctx.timing(False)
     fam = {}
-    for f in ("sweep_energy", "sweep_forces", "sweep_rates", "bin_", "relax_", "misc_", "select", "probe"):
+    for f in ("relax_persistent", "sweep_energy", "sweep_forces", "sweep_rates", "bin_", "line_", "misc_", "select", "probe", "hop_"):
         ms, cnt = ctx.timing_read(f)
         fam[f] = {"ms": ms, "launches": cnt}
     ctx.timing_reset()
-    clocks = sampler.stop()
 
-    # ---- timed region 2: through the host API (upload from pinned memory, event, read back)
-    host = torch.from_numpy(sim.adatoms.copy()).pin_memory()
+    # ---- timed region 2: the same events through the host API (upload from pinned memory, event, read back)
+    host = torch.from_numpy(state0.copy()).pin_memory()
     n_at = host.numel() // 2
     barrier()
     t0 = time.perf_counter()
@@ -254,7 +259,7 @@ def run_ours(args):
     for s in range(args.steps):
         ctx.state_set(host.numpy())
         h2d += host.numel() * 8
-        rec = sim.step(us[nsteps + s, 0], us[nsteps + s, 1], cap)
+        rec = sim.step(us[args.warmup + s, 0], us[args.warmup + s, 1], cap)
         out = ctx.state_get()
         d2h += out.size * 8
         if out.size == host.numel():
@@ -263,6 +268,7 @@ def run_ours(args):
             host = torch.from_numpy(out.copy()).pin_memory()
     barrier()
     t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop(t_begin1, t_end)
 
     tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -273,9 +279,14 @@ def run_ours(args):
         peaks, peak_src = load_peaks()
         ls = [r["line_searches"] for r in recs]
         ls_mean = float(np.mean(ls)) if ls else 0.0
-        abytes, binfo = algorithmic_bytes_line_energy(gv, sub, ad0)
-        ek = fam["sweep_energy"]
+        # dominant kernel: the persistent relaxation kernel; one launch = one Relaxation = `ls` line searches, each
+        # the 20-candidate energy (32 B/adatom + 16 B/active substrate atom + 8 B/cell + 160 B) plus one force
+        # sweep (40 B/adatom + 16 B/active substrate atom + 8 B/cell)  -- SURVEY.md 8d
+        abytes_line, binfo = algorithmic_bytes_line_energy(gv, sub, ad0)
+        abytes_force = 40 * binfo["n_adatoms"] + 16 * binfo["n_substrate_active"] + 8 * binfo["cells_touched"]
+        ek = fam["relax_persistent"]
         k_ms = ek["ms"] / max(ek["launches"], 1)
+        abytes = (abytes_line + abytes_force) * ls_mean
         achieved = abytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         total_kernel_ms = sum(v["ms"] for v in fam.values())
         value = world * args.steps / t_dev
@@ -297,13 +308,14 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": int(launches), "wall_s_timed_region": wall_dev,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_sweep_energy (20 candidate configurations per launch)",
+            "roofline": {"bound": "hbm", "kernel": "k_relax2 (persistent: one launch = one Relaxation; per line search 20 candidate energies + 1 force sweep)",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": abytes, "bytes_detail": binfo,
                          "avg_launch_us": k_ms * 1e3, "launches": ek["launches"],
                          "kernel_share_of_gpu_time": ek["ms"] / total_kernel_ms if total_kernel_ms else None,
                          "binding_roof": "fp64 pipe (about 80 flop per algorithmic byte, SURVEY.md §8d)",
-                         "fp64_gflops": (10 + 14 * 20) * pr["energy"] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0},
+                         "algorithmic_bytes_per_line_search": abytes_line + abytes_force,
+                         "fp64_gflops": ((10 + 14 * 20) * pr["energy"] + 24 * pr["forces"]) * ls_mean / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0},
             "kernel_families_ms": {k: round(v["ms"], 3) for k, v in fam.items()},
             "cpu_baseline": cpu,
             "prerelax": {"line_searches": int(st.line_searches), "status": int(st.status)},
@@ -330,7 +342,7 @@ def pairs_per_sweep(ctx, sim):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_256x256_10k")

@@ -965,13 +965,12 @@ static int relax_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, double
 }
 
 // second-generation persistent kernel (kmc_relax2.cuh): cell-sorted state, balanced work items
-template <int G>
 static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
     void* args[] = {(void*)&R};
     c->launches++;
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->timing) { cudaEventCreate(&ea); cudaEventCreate(&eb); cudaEventRecord(ea, c->stream); }
-    CK(cudaLaunchCooperativeKernel((const void*)k_relax2<G>, dim3(blocks), dim3(R2_THREADS), args, 0, c->stream));
+    CK(cudaLaunchCooperativeKernel((const void*)k_relax2, dim3(blocks), dim3(R2_THREADS), args, 0, c->stream));
     if (c->timing) { cudaEventRecord(eb, c->stream); c->recs.push_back({family_id(c, "relax_persistent"), ea, eb}); }
     return 0;
 }
@@ -981,9 +980,7 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
     const int n = (int)c->st_n;
     if (n == 0) { if (stats) *stats = st; return 0; }
     const int blocks = std::min(c->sm_count, std::max(1, (n + 15) / 16));
-    const int gthreads = blocks * R2_THREADS;
-    int G = 32;
-    while (G > 1 && (long long)n * G > gthreads) G >>= 1;
+    const int G = 0;
     if (c->item_cap == 0) c->item_cap = (size_t)n * 4 + (size_t)c->dp.ncell * 2 + 1024;
     for (int attempt = 0; attempt < 8; ++attempt) {
         Relax2Args R{};
@@ -1019,14 +1016,8 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         R.stats = (KmcRelaxStatsDev*)(sync + 64);
         R.phase_ns = (unsigned long long*)(sync + 128);
         R.scale0 = scale0; R.threshold0 = threshold0; R.max_ls = max_ls;
-        switch (G) {
-            case 32: TRY(launch_relax2<32>(c, R, blocks)); break;
-            case 16: TRY(launch_relax2<16>(c, R, blocks)); break;
-            case 8: TRY(launch_relax2<8>(c, R, blocks)); break;
-            case 4: TRY(launch_relax2<4>(c, R, blocks)); break;
-            case 2: TRY(launch_relax2<2>(c, R, blocks)); break;
-            default: TRY(launch_relax2<1>(c, R, blocks)); break;
-        }
+        R.phase_block = getenv("KMC_PHASE_BLOCK") ? std::min(atoi(getenv("KMC_PHASE_BLOCK")), blocks - 1) : 0;
+        TRY(launch_relax2(c, R, blocks));
         TRY(mail(c, sync, 256));
         const char* hm = (const char*)c->h_mail;
         const KmcRelaxStatsDev* ds = (const KmcRelaxStatsDev*)(hm + 64);
@@ -1039,9 +1030,9 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         if (getenv("KMC_PHASE_TIMING")) {
             const unsigned long long* ph = (const unsigned long long*)(hm + 128);
             const double nls = ds->line_searches > 0 ? (double)ds->line_searches : 1.0;
-            fprintf(stderr, "[kmc2 phase us/ls] E %.2f | bar %.2f | fix+bar %.2f | S %.2f | bar %.2f | G %.2f | bar %.2f  (ls=%lld blocks=%d G=%d items=%d)\n",
+            fprintf(stderr, "[kmc2 phase us/ls] E %.2f | bar %.2f | fix+bar %.2f | S %.2f | bar %.2f | G %.2f | bar %.2f | rebuild %.2f (%.1f us each, %lld) movers/ls %.1f (ls=%lld restarts=%lld blocks=%d G=%d items=%d)\n",
                     ph[0] / nls * 1e-3, ph[1] / nls * 1e-3, ph[2] / nls * 1e-3, ph[3] / nls * 1e-3, ph[4] / nls * 1e-3, ph[5] / nls * 1e-3,
-                    ph[6] / nls * 1e-3, (long long)ds->line_searches, blocks, G, *(const int*)(hm + 20));
+                    ph[6] / nls * 1e-3, ph[7] / nls * 1e-3, ph[8] ? ph[7] * 1e-3 / ph[8] : 0.0, (long long)ph[8], ph[9] / nls, (long long)ds->line_searches, (long long)ds->restarts, blocks, G, *(const int*)(hm + 20));
         }
         st.line_searches = ds->line_searches; st.restarts = ds->restarts; st.maxF = ds->maxF;
         st.final_threshold = ds->final_threshold; st.final_scale = ds->final_scale; st.status = ds->status;

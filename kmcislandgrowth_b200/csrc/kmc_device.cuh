@@ -125,6 +125,17 @@ __device__ __forceinline__ int stencil_population(const DevParams& P, const Cell
     return m;
 }
 
+// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (x is a squared distance: finite, > 0 where used)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
 // ---- Lennard-Jones pair terms on r^2 (Energy.py:24,28 and :55-59) ------------------------------
 // E*((r0/r)^12 - 2 (r0/r)^6) = E*q6*(q6-2) with q6 = (r0^2/r^2)^3 ; zero when r == 0.
 __device__ __forceinline__ double lj_energy(double r2, double E, double r0sq) {
@@ -138,7 +149,7 @@ __device__ __forceinline__ double lj_energy(double r2, double E, double r0sq) {
 // r < 1e-2 are skipped (Energy.py:55), i.e. r^2 < 1e-4.
 __device__ __forceinline__ double lj_force_coef(double r2, double E, double r0sq) {
     if (r2 < 1e-4) return 0.0;
-    const double inv = 1.0 / r2;
+    const double inv = fast_rcp(r2);
     const double q2 = r0sq * inv;
     const double q6 = q2 * q2 * q2;
     return 12.0 * E * (q6 - q6 * q6) * inv;

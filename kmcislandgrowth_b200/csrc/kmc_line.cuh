@@ -28,18 +28,6 @@ __device__ __forceinline__ double2 cand2(double2 p, double2 s, int a, double sca
     return make_double2(cand1(p.x, s.x, a, scale), cand1(p.y, s.y, a, scale));
 }
 
-// 1/x to ~1 ulp: MUFU.RCP64H seed (2^-23) + two Newton steps (no IEEE corner cases needed: x is a
-// squared distance, finite and > 0 where the result is used)
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
-}
-
 // energies of one pair for all KC candidates: displacement d0 + a*dd (d0 already min-image wrapped).
 // Stable pairs (the wrap cannot change along the line) use r^2(a) = A + a(B + aC).
 __device__ __forceinline__ void pair_line(const DevParams& P, double dx0, double dy0, double ddx, double ddy, double E,
@@ -63,6 +51,35 @@ __device__ __forceinline__ void pair_line(const DevParams& P, double dx0, double
             const double dx = put_in_box(fma((double)a, ddx, dx0), P.L, P.halfL);
             const double dy = fma((double)a, ddy, dy0);
             acc[a] += lj_energy(dx * dx + dy * dy, E, r0sq);
+        }
+    }
+}
+
+// the same for the NC candidates a0 .. a0+NC-1 only (two lanes share one pair in the persistent kernel:
+// half the accumulators per lane, twice the warps per SM)
+template <int NC>
+__device__ __forceinline__ void pair_line_part(const DevParams& P, double dx0, double dy0, double ddx, double ddy, double E,
+                                               double r0sq, int a0, double (&acc)[NC]) {
+    const double reach = fabs(dx0) + (KC - 1) * fabs(ddx);
+    if (reach < P.halfL - 1e-9) {
+        const double bx = fma((double)a0, ddx, dx0), by = fma((double)a0, ddy, dy0);   // displacement at candidate a0
+        const double A = bx * bx + by * by;
+        const double B = 2.0 * (bx * ddx + by * ddy);
+        const double C = ddx * ddx + ddy * ddy;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double r2 = fma((double)k, fma((double)k, C, B), A);
+            const double q2 = r0sq * fast_rcp(r2);
+            const double q6 = q2 * q2 * q2;
+            const double e = q6 * (q6 - 2.0);
+            acc[k] = (r2 > 0.0) ? fma(E, e, acc[k]) : acc[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double dx = put_in_box(fma((double)(a0 + k), ddx, dx0), P.L, P.halfL);
+            const double dy = fma((double)(a0 + k), ddy, dy0);
+            acc[k] += lj_energy(dx * dx + dy * dy, E, r0sq);
         }
     }
 }

@@ -19,14 +19,19 @@
 namespace kmc {
 
 constexpr int R2_THREADS = 512;
+constexpr int R2_LP = 1;            // lanes per pair in the energy phase
+constexpr int R2_NC = KC / R2_LP;   // candidates per lane
 constexpr int R2_CHUNK = 64;        // pairs per work item
 constexpr int R2_PARTS = 8;         // per home cell: adatom columns 0..3, substrate columns 0..3
 
 struct WorkItem {
-    int cell;      // home cell
-    int part;      // 0..3 adatom partner column, 4..7 substrate partner column
-    int begin;     // first pair of the chunk in the (home x partner) pair space
-    int count;     // pairs in the chunk
+    int hb, nh;            // home atoms: slots [hb, hb+nh)
+    int b0, n0, b1, n1, b2; // partner slot ranges [b0,b0+n0) [b1,b1+n1) [b2,...) in stencil order
+    int kind;              // bit 0..2: range k is the home cell itself (pair only if slot_i < slot_j); bit 3: substrate partners
+    int begin;             // first pair of the chunk in the (home x partner) pair space, pair q = i + nh*j
+    int count;             // pairs in the chunk
+    float inv_nh;          // 1/nh for the index split
+    int pad;
 };
 
 struct Relax2Args {
@@ -60,6 +65,7 @@ struct Relax2Args {
     long long max_ls;
     KmcRelaxStatsDev* stats;
     unsigned long long* phase_ns;
+    int phase_block;        // which block's thread 0 keeps the phase timers (diagnostics)
 };
 
 struct Relax2Smem {
@@ -230,9 +236,14 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         const int nh = R.start[c + 1] - R.start[c];
         const Ranges r = partner_ranges(P, R.start, R.sub.start, c, part);
         const int pairs = nh * r.total;
+        WorkItem it;
+        it.hb = R.start[c]; it.nh = nh;
+        it.b0 = r.b[0]; it.n0 = r.e[0] - r.b[0]; it.b1 = r.b[1]; it.n1 = r.e[1] - r.b[1]; it.b2 = r.b[2];
+        it.kind = r.self[0] | (r.self[1] << 1) | (r.self[2] << 2) | (part >= 4 ? 8 : 0);
+        it.inv_nh = 1.0f / (float)nh;
+        it.pad = 0;
         for (int k = first; k < last && k < R.item_cap; ++k) {
-            WorkItem it;
-            it.cell = c; it.part = part; it.begin = (k - first) * R2_CHUNK;
+            it.begin = (k - first) * R2_CHUNK;
             it.count = min(R2_CHUNK, pairs - it.begin);
             R.items[k] = it;
         }
@@ -240,32 +251,32 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
     grid_barrier(R.barrier, epoch);
 }
 
-// ---- E: one work item, 32 lanes -----------------------------------------------------------------
-__device__ __forceinline__ void relax2_item(const Relax2Args& R, const WorkItem it, const double2* pos, const double2* sdir,
-                                            double inv_step, int lane, double (&acc)[KC]) {
+// ---- E: one work item ----------------------------------------------------------------------------
+__device__ __forceinline__ void relax2_item(const Relax2Args& R, const WorkItem& it, const double2* pos, const double2* sdir,
+                                            double inv_step, int lane, double (&acc)[R2_NC]) {
     const DevParams& P = R.P;
-    const int hb = R.start[it.cell], nh = R.start[it.cell + 1] - hb;
-    const Ranges r = partner_ranges(P, R.start, R.sub.start, it.cell, it.part);
-    const bool is_sub = it.part >= 4;
-    const int n0 = r.e[0] - r.b[0], n1 = r.e[1] - r.b[1];
-    for (int q = it.begin + lane; q < it.begin + it.count; q += 32) {
-        const int i = q % nh, j = q / nh;
-        const int hs = hb + i;
+    const bool is_sub = (it.kind & 8) != 0;
+    const int a0 = (lane & (R2_LP - 1)) * R2_NC;
+    for (int q = it.begin + lane / R2_LP; q < it.begin + it.count; q += 32 / R2_LP) {
+        int j = (int)((float)q * it.inv_nh);                    // q / nh with one fix-up step (pair spaces stay far below 2^23)
+        int i = q - j * it.nh;
+        if (i < 0) { --j; i += it.nh; } else if (i >= it.nh) { ++j; i -= it.nh; }
+        const int hs = it.hb + i;
         int js, self;
-        if (j < n0) { js = r.b[0] + j; self = r.self[0]; }
-        else if (j < n0 + n1) { js = r.b[1] + (j - n0); self = r.self[1]; }
-        else { js = r.b[2] + (j - n0 - n1); self = r.self[2]; }
+        if (j < it.n0) { js = it.b0 + j; self = it.kind & 1; }
+        else if (j < it.n0 + it.n1) { js = it.b1 + (j - it.n0); self = it.kind & 2; }
+        else { js = it.b2 + (j - it.n0 - it.n1); self = it.kind & 4; }
         if (R.flag[hs]) continue;                               // movers are handled by the fix-up phase
         const double2 pi = pos[hs], si = sdir[hs];
         if (is_sub) {
             const double2 pj = R.sub.sxy[js];
             const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
-            pair_line(P, dx0, pj.y - pi.y, -si.x * inv_step, -si.y * inv_step, P.E_as, P.ras2, acc);
+            pair_line_part<R2_NC>(P, dx0, pj.y - pi.y, -si.x * inv_step, -si.y * inv_step, P.E_as, P.ras2, a0, acc);
         } else {
             if (R.flag[js] || (self && js <= hs)) continue;
             const double2 pj = pos[js], sj = sdir[js];
             const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
-            pair_line(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, acc);
+            pair_line_part<R2_NC>(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, a0, acc);
         }
     }
 }
@@ -318,20 +329,32 @@ __device__ __forceinline__ uint8_t mover_flag(const DevParams& P, double2 p0, do
 // ---- G: forces at `pos` (+ optional fused CG update / mover flags) --------------------------------
 // mode 0: sdir <- F (the first direction dx0, 2DGrowth.py:120,125), count pairs when asked
 // mode 1: max|F|^2 partial, sdir <- F + beta*sdir (2DGrowth.py:147), flag <- mover test of the next line
-template <int G>
+__device__ __forceinline__ double group_sum_rt(double v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Every block owns a contiguous chunk of slots (cell-sorted, so its atoms share stencils in L1).  The chunk is
+// processed in rounds; each round gives every atom G lanes, G = the largest power of two that lets the round
+// cover at least half of what is left (64 atoms x 8 lanes, then 4 atoms x 32 lanes for 68 atoms on 512 threads).
 __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2* pos, double2* sdir, const int* oidx, int mode, double beta,
                                               double scale, bool count_pairs, Relax2Smem& S) {
     const DevParams& P = R.P;
-    const int lane = threadIdx.x & (G - 1);
-    const int ggroups = (gridDim.x * blockDim.x) / G;
-    const int rounds = (R.n + ggroups - 1) / ggroups;
+    const int T = blockDim.x;
+    const int per = (R.n + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
     CellView ad;
     ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = R.n;
     double mf = 0.0;
     unsigned long long visits = 0;
-    for (int rd = 0; rd < rounds; ++rd) {
-        const int slot = rd * ggroups + (blockIdx.x * blockDim.x + threadIdx.x) / G;
-        const bool live = slot < R.n;
+    for (int r0 = lo; r0 < hi;) {
+        const int rem = hi - r0;
+        int G = 32;
+        while (G > 1 && (T / G) * 2 < rem) G >>= 1;       // T/G groups must cover >= rem/2
+        const int groups = T / G;
+        const int lane = threadIdx.x & (G - 1);
+        const int slot = r0 + threadIdx.x / G;
+        const bool live = slot < hi;
         double ax = 0, ay = 0, sx = 0, sy = 0;
         double2 pi = make_double2(0, 0);
         if (live) {
@@ -350,8 +373,8 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
                 ++visits;
             });
         }
-        ax = group_sum<G>(ax); ay = group_sum<G>(ay);
-        sx = group_sum<G>(sx); sy = group_sum<G>(sy);
+        ax = group_sum_rt(ax, G); ay = group_sum_rt(ay, G);
+        sx = group_sum_rt(sx, G); sy = group_sum_rt(sy, G);
         if (live && lane == 0) {
             const double fx = ax + sx, fy = ay + sy;                // 2DGrowth.py:120
             double2 sn;
@@ -365,6 +388,7 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
             sdir[slot] = sn;
             R.flag[slot] = mover_flag(P, pi, sn, scale);
         }
+        r0 += groups;
     }
     if (mode == 1) {
         const double r_mf = block_max(mf, S.red);
@@ -377,13 +401,12 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
 }
 
 #define PHASE2_MARK(k)                                             \
-    if (gtid == 0) {                                               \
+    if (threadIdx.x == 0 && blockIdx.x == R.phase_block) {                                               \
         const unsigned long long _t = gtimer();                    \
         R.phase_ns[k] += _t - t_mark;                              \
         t_mark = _t;                                               \
     }
 
-template <int G>
 __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     __shared__ Relax2Smem S;
     unsigned int epoch = 0;
@@ -402,6 +425,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     double maxF = 0.0, lastmaxF = 0.0;
     bool first_pass = true;
     bool overflow = false;
+    long long rebuilds = 0, mover_sum = 0;
     unsigned long long t_mark = gtimer();
 
     // candidate sums, argmin, x_np, partial reductions; returns after the barrier that publishes x_np
@@ -432,25 +456,36 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 if (R.flag[i]) R.movers[p++] = i;
             if (t == T - 1) *R.n_movers = S.scan[t];
         }
-        double acc[KC];
+        double acc[R2_NC];
 #pragma unroll
-        for (int a = 0; a < KC; ++a) acc[a] = 0.0;
+        for (int a = 0; a < R2_NC; ++a) acc[a] = 0.0;
         const int n_items = *R.n_items;
-        for (int k = gwarp; k < n_items; k += nwarps) relax2_item(R, R.items[k], pos, sdir, inv_step, lane, acc);
+        {   // block 0 builds the mover list; when other blocks exist they share the items among themselves
+            const int wpb = R2_THREADS / 32;
+            const int w0 = nblk > 1 ? gwarp - wpb : gwarp, nw = nblk > 1 ? nwarps - wpb : nwarps;
+            if (w0 >= 0)
+                for (int k = w0; k < n_items; k += nw) {
+                    const WorkItem it = R.items[k];
+                    relax2_item(R, it, pos, sdir, inv_step, lane, acc);
+                }
+        }
         if (P.aa_mode == 0) {
+            const int a0 = (lane & (R2_LP - 1)) * R2_NC;
             for (int i = gwarp; i < R.n; i += nwarps) {
                 const double2 pi = pos[i], si = sdir[i];
-                for (int j = i + 1 + lane; j < R.n; j += 32) {
+                for (int j = i + 1 + lane / R2_LP; j < R.n; j += 32 / R2_LP) {
                     const double2 pj = pos[j], sj = sdir[j];
                     const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
-                    pair_line(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, acc);
+                    pair_line_part<R2_NC>(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, a0, acc);
                 }
             }
         }
 #pragma unroll
-        for (int a = 0; a < KC; ++a) {
-            const double v = group_sum<32>(acc[a]);
-            if (lane == 0) S.wred[warp][a] = v;
+        for (int a = 0; a < R2_NC; ++a) {      // sum over the lanes holding the same candidates (same lane parity)
+            double v = acc[a];
+#pragma unroll
+            for (int o = 16; o >= R2_LP; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane < R2_LP) S.wred[warp][lane * R2_NC + a] = v;
         }
         __syncthreads();
         if (threadIdx.x < KC) {
@@ -463,6 +498,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(1)
         // ---------------- F
         const int nm = *R.n_movers;
+        mover_sum += nm;
         if (nm > 0) {
             for (int w = gwarp; w < nm * KC; w += nwarps) {
                 const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane);
@@ -529,10 +565,12 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S);
             if (gtid == 0) *R.need_rebuild = 0;
             if (*R.n_items > R.item_cap) overflow = true;
+            ++rebuilds;
+            PHASE2_MARK(7)
             cs ^= 1;          // the rebuilt x_np now lives in pos[cur]: make it the "next" buffer by flipping cur
             cur ^= 1;
         }
-        relax2_forces<G>(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S);
+        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S);
         PHASE2_MARK(5)
         grid_barrier(R.barrier, epoch);
         PHASE2_MARK(6)
@@ -550,7 +588,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         if (scale > 1024) { scale = 16; threshold *= 10; }              // :111-113
         relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S);
         if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
-        relax2_forces<G>(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S);   // dx0, sn = dx0  :120,125
+        relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S);   // dx0, sn = dx0  :120,125
         first_pass = false;
         grid_barrier(R.barrier, epoch);
         line_search();                                                  // :121-129
@@ -589,6 +627,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         R.stats->final_threshold = threshold;
         R.stats->final_scale = scale;
         R.stats->status = status;
+        R.phase_ns[8] = (unsigned long long)rebuilds;
+        R.phase_ns[9] = (unsigned long long)mover_sum;
     }
 }
 
