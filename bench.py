@@ -152,7 +152,7 @@ def run_reference(args):
     from kmcislandgrowth_b200 import workloads
     gv, sub, ad = workloads.make(args.workload)
     rng = np.random.default_rng(1234)
-    fx = load_fixture(args.workload)
+    fx = load_fixture(args.workload, args.warmup, args.steps)
     vals = []
     info = None
     for s in range(args.warmup + args.steps):
@@ -180,10 +180,18 @@ def workload_config(name, gv, ad):
             "l2_note": "working set (<2 MB) fits L2 by construction of the workload; every launch re-reads positions that the previous launch rewrote"}
 
 
-def load_fixture(name):
+def load_fixture(name, first=0, count=None):
+    """line searches per event of the seeded bench trajectory, recorded on the GPU with --record-fixture
+    (a property of the workload: the CPU oracle follows the same trajectory, tests/test_gpu_parity.py)"""
     path = os.path.join(ROOT, "tests", "golden", "bench_%s.json" % name)
     if os.path.exists(path):
-        return json.load(open(path))
+        fx = json.load(open(path))
+        ls = fx.get("line_searches", [])
+        sel = ls[first:first + count] if count else ls[first:]
+        if not sel:
+            sel = ls
+        fx["line_searches_per_event"] = float(np.mean(sel)) if sel else 1500.0
+        return fx
     return {"line_searches_per_event": 1500.0, "note": "default; no fixture recorded yet"}
 
 
@@ -221,6 +229,15 @@ def run_ours(args):
     st = ctx.relax(sim.sbins, 16, 1e-4, args.prerelax)
     nsteps = args.warmup + args.steps
     us = rng.uniform(0, 1, (2 * nsteps, 2))
+    if args.record_fixture and rank == 0:
+        recs = [sim.step(us[s, 0], us[s, 1], cap) for s in range(nsteps)]
+        out = {"workload": args.workload, "prerelax": args.prerelax, "line_searches": [int(r["line_searches"]) for r in recs],
+               "kinds": [int(r["kind"]) for r in recs], "note": "recorded by bench.py --record-fixture on a B200"}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bench_%s.json" % args.workload), "w"))
+        print(json.dumps(out))
+        sim.close()
+        return
     for s in range(args.warmup):
         sim.step(us[s, 0], us[s, 1], cap)
 
@@ -350,6 +367,7 @@ def main():
     ap.add_argument("--prerelax", type=int, default=4000)
     ap.add_argument("--ref-line-searches", type=int, default=6, help="line searches per bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--record-fixture", action="store_true", help="record line searches per event of the seeded trajectory")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

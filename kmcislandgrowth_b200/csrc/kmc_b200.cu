@@ -1116,24 +1116,40 @@ int kmc_deposit_place(KmcCtx* c, const KmcBins* sb, double u) {
 }
 
 // device helper for HopAtom: ordered list of surface atoms within 3 r_a of the jumper, pick int(u*ncand)
-__global__ void k_hop_target(DevParams P, const double2* __restrict__ xy, const uint8_t* __restrict__ surf, int n, int k, double u,
-                             double* __restrict__ out /* [0]=ncand [1]=tx [2]=ty */) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(1024) k_hop_target(DevParams P, const double2* __restrict__ xy, const uint8_t* __restrict__ surf, int n, int k, double u,
+                                                     double* __restrict__ out /* [0]=ncand [1]=tx [2]=ty */) {
+    // one block: every thread owns a contiguous slice (keeps the candidates in adatom order, 2DGrowth.py:244-246)
+    __shared__ int s_scan[1024];
+    const int T = blockDim.x, t = threadIdx.x;
     const double2 j = xy[k];
     const double cut = 3 * P.r_a;
-    int ncand = 0;
-    for (int i = 0; i < n; ++i)
-        if (surf[i] && sqrt(dist2_exact(P, j.x, j.y, xy[i].x, xy[i].y)) < cut) ++ncand;
-    out[0] = ncand;
+    const int per = (n + T - 1) / T;
+    const int lo = t * per, hi = min(lo + per, n);
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i)
+        if (surf[i] && sqrt(dist2_exact(P, j.x, j.y, xy[i].x, xy[i].y)) < cut) ++cnt;
+    s_scan[t] = cnt;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {
+        int v = (t >= off) ? s_scan[t - off] : 0;
+        __syncthreads();
+        s_scan[t] += v;
+        __syncthreads();
+    }
+    const int ncand = s_scan[T - 1];
+    if (t == 0) out[0] = ncand;
     if (ncand == 0) return;
-    int pick = (int)(u * (double)ncand);
+    int pick = (int)(u * (double)ncand);                                  // randint(0, ncand-1) -> int(u*ncand)
     if (pick >= ncand) pick = ncand - 1;
-    int seen = 0;
-    for (int i = 0; i < n; ++i)
-        if (surf[i] && sqrt(dist2_exact(P, j.x, j.y, xy[i].x, xy[i].y)) < cut) {
-            if (seen == pick) { out[1] = xy[i].x; out[2] = xy[i].y; return; }
-            ++seen;
-        }
+    const int before = s_scan[t] - cnt;
+    if (pick >= before && pick < before + cnt) {
+        int seen = before;
+        for (int i = lo; i < hi; ++i)
+            if (surf[i] && sqrt(dist2_exact(P, j.x, j.y, xy[i].x, xy[i].y)) < cut) {
+                if (seen == pick) { out[1] = xy[i].x; out[2] = xy[i].y; }
+                ++seen;
+            }
+    }
 }
 
 __global__ void k_remove_atom(const double2* __restrict__ in, int n, int k, double2* __restrict__ out) {
@@ -1150,7 +1166,7 @@ int kmc_hop_place(KmcCtx* c, const KmcBins* sb, int64_t k, double u) {
     TRY(slot(c, S_OUT1, (size_t)n, &surf));
     TRY(slot(c, S_TMP0, 8, &tmp));
     TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, nullptr, surf, nullptr, nullptr, nullptr, nullptr, nullptr));   // :239
-    LAUNCH(c, "hop_target", k_hop_target, 1, 32, c->dp, (const double2*)c->st_xy, surf, n, (int)k, u, tmp);          // :240-248
+    LAUNCH(c, "hop_target", k_hop_target, 1, 1024, c->dp, (const double2*)c->st_xy, surf, n, (int)k, u, tmp);          // :240-248
     CK(cudaGetLastError());
     TRY(mail(c, tmp, 3 * sizeof(double)));
     const double* hm = (const double*)c->h_mail;
