@@ -195,6 +195,7 @@ static DevParams to_dev(const KmcParams& p) {
     d.beta = p.beta; d.omega = p.omega; d.Rd = p.Rd;
     d.nbx = p.nbins_x; d.nby = p.nbins_y; d.ncell = p.nbins_x * p.nbins_y;
     d.aa_mode = p.aa_mode;
+    d.precision = p.precision;
     return d;
 }
 
@@ -204,7 +205,7 @@ static int check_params(const KmcParams* p) {
     if (p->nbins_x < 3 || p->nbins_y < 1) return fail(KMC_E_ARG, "need nbins_x >= 3 and nbins_y >= 1 (got %d x %d)", p->nbins_x, p->nbins_y);
     if ((int64_t)p->nbins_x * p->nbins_y > (1 << 28)) return fail(KMC_E_ARG, "cell grid too large");
     if (p->aa_mode != 0 && p->aa_mode != 1) return fail(KMC_E_ARG, "aa_mode must be 0 or 1");
-    if (p->precision != 0) return fail(KMC_E_ARG, "precision %d not built in this revision (fp64 only)", p->precision);
+    if (p->precision != 0 && p->precision != 1) return fail(KMC_E_ARG, "precision must be 0 (fp64) or 1 (fp32 pair terms)");
     return 0;
 }
 
@@ -1016,6 +1017,7 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         R.stats = (KmcRelaxStatsDev*)(sync + 64);
         R.phase_ns = (unsigned long long*)(sync + 128);
         R.scale0 = scale0; R.threshold0 = threshold0; R.max_ls = max_ls;
+        R.debug = getenv("KMC_DEBUG_E") ? atoi(getenv("KMC_DEBUG_E")) : 0;
         R.phase_block = getenv("KMC_PHASE_BLOCK") ? std::min(atoi(getenv("KMC_PHASE_BLOCK")), blocks - 1) : 0;
         TRY(launch_relax2(c, R, blocks));
         TRY(mail(c, sync, 256));

@@ -18,6 +18,7 @@ struct DevParams {
     double beta, omega, Rd;
     int nbx, nby, ncell;     // ncell = nbx*nby ; cell id ncell = atoms outside the addressable grid
     int aa_mode;
+    int precision;           // 0: fp64 pair terms; 1: fp32 pair terms on fp64-formed displacements, fp64 accumulation
 };
 
 // A cell list: atoms sorted by cell (column-major nx*nby+ny, input order kept inside a cell).
@@ -153,6 +154,24 @@ __device__ __forceinline__ double lj_force_coef(double r2, double E, double r0sq
     const double q2 = r0sq * inv;
     const double q6 = q2 * q2 * q2;
     return 12.0 * E * (q6 - q6 * q6) * inv;
+}
+
+// fp32 pair terms (precision 1): the min-image displacement is formed in fp64, then the LJ term is evaluated
+// in single precision (relative error ~1e-6 per term) and accumulated by the caller in fp64.
+__device__ __forceinline__ double lj_energy_f32(double dx, double dy, double E, double r0sq) {
+    const float fx = (float)dx, fy = (float)dy;
+    const float r2 = fx * fx + fy * fy;
+    if (!(r2 > 0.0f)) return 0.0;
+    const float q2 = __fdividef((float)r0sq, r2);
+    const float q6 = q2 * q2 * q2;
+    return (double)((float)E * (q6 * (q6 - 2.0f)));
+}
+__device__ __forceinline__ float lj_force_coef_f32(float r2, float E, float r0sq) {
+    if (r2 < 1e-4f) return 0.0f;
+    const float inv = __fdividef(1.0f, r2);
+    const float q2 = r0sq * inv;
+    const float q6 = q2 * q2 * q2;
+    return 12.0f * E * (q6 - q6 * q6) * inv;
 }
 
 // exact squared distance the way the reference forms it (Periodic.py:58-59: d*=d ; d[2j]+d[2j+1]),

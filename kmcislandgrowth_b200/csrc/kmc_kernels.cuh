@@ -134,6 +134,13 @@ __device__ __forceinline__ void acc_force(const DevParams& P, double xi, double 
                                           double& fx, double& fy) {
     const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
     const double dy = pj.y - yi;
+    if (P.precision == 1) {
+        const float ex = (float)dx, ey = (float)dy;
+        const float c = lj_force_coef_f32(ex * ex + ey * ey, (float)E, (float)r0sq);
+        fx += (double)(ex * c);
+        fy += (double)(ey * c);
+        return;
+    }
     const double r2 = dx * dx + dy * dy;
     const double c = lj_force_coef(r2, E, r0sq);
     fx += dx * c;
@@ -143,6 +150,7 @@ __device__ __forceinline__ void acc_force(const DevParams& P, double xi, double 
 __device__ __forceinline__ double pair_energy(const DevParams& P, double xi, double yi, double2 pj, double E, double r0sq) {
     const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
     const double dy = pj.y - yi;
+    if (P.precision == 1) return lj_energy_f32(dx, dy, E, r0sq);
     return lj_energy(dx * dx + dy * dy, E, r0sq);
 }
 

@@ -66,6 +66,7 @@ struct Relax2Args {
     KmcRelaxStatsDev* stats;
     unsigned long long* phase_ns;
     int phase_block;        // which block's thread 0 keeps the phase timers (diagnostics)
+    int debug;              // diagnostics only: 1 = energy phase skips the pair arithmetic, 2 = skips the work items
 };
 
 struct Relax2Smem {
@@ -276,6 +277,7 @@ __device__ __forceinline__ void relax2_item(const Relax2Args& R, const WorkItem&
             if (R.flag[js] || (self && js <= hs)) continue;
             const double2 pj = pos[js], sj = sdir[js];
             const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
+            if (R.debug == 1) { acc[0] += dx0 + sj.x + sj.y + pj.y; continue; }
             pair_line_part<R2_NC>(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, a0, acc);
         }
     }
@@ -329,6 +331,41 @@ __device__ __forceinline__ uint8_t mover_flag(const DevParams& P, double2 p0, do
 // ---- G: forces at `pos` (+ optional fused CG update / mover flags) --------------------------------
 // mode 0: sdir <- F (the first direction dx0, 2DGrowth.py:120,125), count pairs when asked
 // mode 1: max|F|^2 partial, sdir <- F + beta*sdir (2DGrowth.py:147), flag <- mover test of the next line
+// forces of the stencil atoms of list `cv` on (xi, yi): same visiting order as visit_stencil, but four
+// neighbour loads are issued before their arithmetic (after a grid barrier every first touch is an L2 hit,
+// and one load in flight per lane made this phase latency bound)
+__device__ __forceinline__ void stencil_forces(const DevParams& P, const CellView& cv, const Stencil& st, int lane, int G, double xi, double yi,
+                                               double E, double r0sq, double& fx, double& fy, unsigned long long& visits) {
+    const bool ycontig = (st.ys[0] >= 0) && (st.ys[2] < P.nby) && (st.ys[1] == st.ys[0] + 1) && (st.ys[2] == st.ys[1] + 1);
+    for (int a = 0; a < st.nxs; ++a) {
+        const int cx = st.xs[a];
+        if (cx < 0 || cx >= P.nbx) continue;
+        const int base = cx * P.nby;
+        const int nseg = ycontig ? 1 : 3;
+        for (int c = 0; c < nseg; ++c) {
+            int b, e;
+            if (ycontig) { b = cv.start[base + st.ys[0]]; e = cv.start[base + st.ys[2] + 1]; }
+            else {
+                const int cy = st.ys[c];
+                if (cy < 0 || cy >= P.nby) continue;
+                b = cv.start[base + cy]; e = cv.start[base + cy + 1];
+            }
+            for (int s = b + lane; s < e; s += 4 * G) {
+                const int s1 = s + G, s2 = s + 2 * G, s3 = s + 3 * G;
+                const double2 p0 = cv.sxy[s];
+                const double2 p1 = cv.sxy[min(s1, e - 1)];
+                const double2 p2 = cv.sxy[min(s2, e - 1)];
+                const double2 p3 = cv.sxy[min(s3, e - 1)];
+                acc_force(P, xi, yi, p0, E, r0sq, fx, fy);
+                if (s1 < e) acc_force(P, xi, yi, p1, E, r0sq, fx, fy);
+                if (s2 < e) acc_force(P, xi, yi, p2, E, r0sq, fx, fy);
+                if (s3 < e) acc_force(P, xi, yi, p3, E, r0sq, fx, fy);
+                visits += 1 + (s1 < e) + (s2 < e) + (s3 < e);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ double group_sum_rt(double v, int G) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -363,15 +400,9 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
             if (P.aa_mode == 0) {
                 for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
             } else {
-                visit_stencil(P, ad, st, lane, G, [&](int s) {
-                    acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
-                    ++visits;
-                });
+                if (R.debug != 3) stencil_forces(P, ad, st, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
             }
-            visit_stencil(P, R.sub, st, lane, G, [&](int s) {
-                acc_force(P, pi.x, pi.y, R.sub.sxy[s], P.E_as, P.ras2, sx, sy);
-                ++visits;
-            });
+            if (R.debug != 3 && R.debug != 5) stencil_forces(P, R.sub, st, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
         }
         ax = group_sum_rt(ax, G); ay = group_sum_rt(ay, G);
         sx = group_sum_rt(sx, G); sy = group_sum_rt(sy, G);
@@ -386,7 +417,7 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
                 sn = make_double2(__dadd_rn(fx, __dmul_rn(beta, so.x)), __dadd_rn(fy, __dmul_rn(beta, so.y)));   // :147
             }
             sdir[slot] = sn;
-            R.flag[slot] = mover_flag(P, pi, sn, scale);
+            R.flag[slot] = (R.debug == 4) ? 0 : mover_flag(P, pi, sn, scale);
         }
         r0 += groups;
     }
@@ -463,7 +494,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         {   // block 0 builds the mover list; when other blocks exist they share the items among themselves
             const int wpb = R2_THREADS / 32;
             const int w0 = nblk > 1 ? gwarp - wpb : gwarp, nw = nblk > 1 ? nwarps - wpb : nwarps;
-            if (w0 >= 0)
+            if (w0 >= 0 && R.debug != 2)
                 for (int k = w0; k < n_items; k += nw) {
                     const WorkItem it = R.items[k];
                     relax2_item(R, it, pos, sdir, inv_step, lane, acc);
@@ -508,6 +539,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             PHASE2_MARK(2)
         }
         // ---------------- S
+        double2 pre_p = make_double2(0, 0), pre_s = make_double2(0, 0);      // issued ahead of the candidate sums
+        if (gtid < R.n) { pre_p = pos[gtid]; pre_s = sdir[gtid]; }
         for (int a = warp; a < KC; a += R2_THREADS / 32) {
             double v = 0.0;
             for (int b = lane; b < nblk; b += 32) v += R.partial[(size_t)a * nblk + b];
@@ -524,8 +557,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         }
         double top = 0.0, bot = 0.0, my = INFINITY;
         for (int slot = gtid; slot < R.n; slot += gthreads) {
-            const double2 p0 = pos[slot];
-            const double2 p = cand2(p0, sdir[slot], amin, dscale);
+            const double2 p0 = (slot == gtid) ? pre_p : pos[slot];
+            const double2 p = cand2(p0, (slot == gtid) ? pre_s : sdir[slot], amin, dscale);
             posn[slot] = p;
             top += p.x * (p.x - p0.x) + p.y * (p.y - p0.y);                // :143
             bot += p0.x * p0.x + p0.y * p0.y;                              // :144

@@ -294,6 +294,47 @@ def test_line_search_candidates_with_cell_crossings(W, Hs, Ha, n, aa, amp):
         ctx.close()
 
 
+@pytest.mark.parametrize("name", ["cfg2_256x256_10k", "cfg3_1024x1024_500k"])
+def test_fp32_vs_fp64_tolerance(name):
+    """BASELINE configs[2]: one force sweep, one configuration energy and one rate table in fp64 and with fp32
+    pair terms, against the fp64 oracle: 1e-6 relative (fp64) / 1e-4 (fp32); bin ids, bond counts and surface
+    flags exact in both (they are always evaluated in fp64)."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv, sub, ad = workloads.make(name)
+    o = _oracle_for(gv)
+    osb = o.PutInBins(sub)
+    Fo = o.AdatomAdatomForces(ad) + o.AdatomSubstrateForces(ad, osb)
+    eo = o.RelaxEnergy((ad, osb))
+    rate_o, surf_o, du_o = o.HoppingRatesDense(ad, osb)
+    ua, ul, ui, du, na, ns = o.Barriers(ad, osb)
+    ocell = o.PutInBins(ad).cell_of_atom()
+    fscale = max(1.0, float(np.max(np.abs(Fo))))
+    worst = {}
+    for prec, tol in ((0, 1e-6), (1, 1e-4)):
+        gv.precision = prec
+        ctx = runtime.Context(runtime.params_from(gv), 0)
+        sb = ctx.bins_create(sub)
+        try:
+            ab = ctx.bins_create(ad)
+            cell = ctx.bins_export(ab)[0]
+            assert np.array_equal(np.where(cell == gv.nbins_x * gv.nbins_y, -1, cell), ocell)
+            ab.close()
+            F = ctx.forces(ad, sb, 3)
+            ferr = float(np.max(np.abs(F - Fo))) / fscale
+            eerr = abs(float(ctx.relax_energy(ad, sb)[0]) - eo) / abs(eo)
+            r = ctx.rates(ad, sb)
+            assert np.array_equal(r["n_a"], na) and np.array_equal(r["n_s"], ns)
+            assert np.array_equal(r["is_surface"].astype(bool), surf_o)
+            rerr = relerr(r["rate"][surf_o], rate_o[surf_o])
+            worst[prec] = (ferr, eerr, rerr)
+            assert ferr < tol and eerr < tol and rerr < tol, (prec, worst)
+        finally:
+            sb.close()
+            ctx.close()
+    print("fp64 / fp32 errors (forces, energy, rates):", worst)
+    assert worst[0][0] < 1e-9 and worst[0][1] < 1e-9       # fp64 is ~1e-13 in practice
+
+
 def test_edge_cases():
     """empty / single-atom inputs and atoms outside the cell grid"""
     from kmcislandgrowth_b200 import Bins, Energy, Growth, Periodic, runtime
