@@ -153,6 +153,11 @@ int kmc_rates(KmcCtx* ctx, const double* xy, int64_t n, const KmcBins* sbins, do
 int kmc_select(KmcCtx* ctx, const double* rate_dense, const uint8_t* is_surface, int64_t n, double u,
                int64_t* result, double* rtot_out, double* pj_out, int mem);
 
+/* 0 (default): sequential-order sums (bit-exact index) up to 65536 adatoms, block scan + search beyond;
+ * 1: always sequential order; 2: always block scan (partial sums associated differently: the index can differ
+ * from the reference's only when r lies within rounding of a partial sum). */
+int kmc_set_select_mode(KmcCtx* ctx, int mode);
+
 /* ---- 2DGrowth.py: events on a device-resident trajectory ---- */
 /* upload / download the adatom array of the context's trajectory (capacity grows on demand) */
 int kmc_state_set(KmcCtx* ctx, const double* xy, int64_t n, int mem);

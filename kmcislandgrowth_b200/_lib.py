@@ -75,6 +75,7 @@ SIGNATURES = {
     "kmc_state_count": (_I64, [_VP]),
     "kmc_relax": (C.c_int, [_VP, _VP, _I32, _D, _I64, C.POINTER(KmcRelaxStats)]),
     "kmc_set_relax_mode": (C.c_int, [_VP, C.c_int]),
+    "kmc_set_select_mode": (C.c_int, [_VP, C.c_int]),
     "kmc_deposit_place": (C.c_int, [_VP, _VP, _D]),
     "kmc_hop_place": (C.c_int, [_VP, _VP, _I64, _D]),
     "kmc_event": (C.c_int, [_VP, _VP, _D, _D, _I64, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_D),

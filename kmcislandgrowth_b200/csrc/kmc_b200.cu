@@ -80,6 +80,7 @@ struct KmcCtx {
     int64_t st_n = 0, st_cap = 0;
     int relax_mode = 2;             // 2: persistent kernel on cell-sorted state (default), 1: first-generation persistent kernel, 0: host-driven loop
     size_t item_cap = 0;
+    int select_mode = 0;            // 0: sequential-order sums up to 65536 atoms, block scan beyond; 1: always sequential; 2: always block scan
     int sm_count = 148;
 };
 
@@ -775,7 +776,19 @@ int kmc_select(KmcCtx* c, const double* rate, const uint8_t* surf, int64_t n, do
     TRY(call.out((long long*)result, 2, S_OUT0, &dres));
     TRY(call.out(rtot, 1, S_OUT1, &drt));
     TRY(call.out(pj, (size_t)n + 1, S_OUT2, &dpj));
-    LAUNCH(c, "select", k_select, 1, 32, c->dp, dr, dsf, (int)n, u, dres, drt, dpj);
+    const bool parallel = !pj && (c->select_mode == 2 || (c->select_mode == 0 && n > 65536));
+    if (parallel) {
+        const int nblocks = (int)std::min<int64_t>(1024, (n + 4095) / 4096);
+        const int chunk = (int)((n + nblocks - 1) / nblocks);
+        double* bsum;
+        int* bcount;
+        TRY(slot(c, S_TMP2, (size_t)nblocks, &bsum));
+        TRY(slot(c, S_TMP3, (size_t)nblocks, &bcount));
+        LAUNCH(c, "select", k_select_block_sums, nblocks, 1024, dr, dsf, (int)n, chunk, bsum, bcount);
+        LAUNCH(c, "select", k_select_final, 1, 1024, c->dp, dr, dsf, (int)n, chunk, nblocks, bsum, bcount, u, dres, drt);
+    } else {
+        LAUNCH(c, "select", k_select, 1, 32, c->dp, dr, dsf, (int)n, u, dres, drt, dpj);
+    }
     CK(cudaGetLastError());
     return call.finish();
 }
@@ -1061,6 +1074,12 @@ int kmc_relax(KmcCtx* c, const KmcBins* sb, int32_t scale0, double threshold0, i
 int kmc_set_relax_mode(KmcCtx* c, int mode) {
     if (!c || mode < 0 || mode > 2) return fail(KMC_E_ARG, "relax mode must be 0 (host-driven), 1 (persistent kernel v1) or 2 (persistent kernel on sorted state)");
     c->relax_mode = mode;
+    return 0;
+}
+
+int kmc_set_select_mode(KmcCtx* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return fail(KMC_E_ARG, "select mode must be 0 (auto), 1 (sequential order) or 2 (block scan)");
+    c->select_mode = mode;
     return 0;
 }
 

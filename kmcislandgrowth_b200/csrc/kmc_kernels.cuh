@@ -401,6 +401,103 @@ __global__ void k_select(DevParams P, const double* __restrict__ rate, const uin
     }
 }
 
+// ---- parallel selection for very large tables (block scan + search) -------------------------------
+// Pass 1: every block sums its contiguous chunk (thread-sequential segments + fixed-tree block sum).
+// Pass 2: one block forms the running sums of the block totals in index order, finds the chunk whose range
+// contains r = u*Rtot, scans that chunk (thread-sequential segments, ordered prefix of the segment totals) and
+// returns the first index with partial sum > r.  Same rule as k_select; the partial sums are associated
+// differently (ulp-level), so the index can differ from the sequential order only when r falls within rounding of
+// a partial sum.  Used by kmc_select for n > 65536 (or on request).
+__global__ void __launch_bounds__(1024) k_select_block_sums(const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, int chunk,
+                                                            double* __restrict__ bsum, int* __restrict__ bcount) {
+    __shared__ double s_red[32];
+    __shared__ int s_cnt[32];
+    const int lo = blockIdx.x * chunk, hi = min(lo + chunk, n);
+    const int per = (chunk + blockDim.x - 1) / blockDim.x;
+    const int a = lo + threadIdx.x * per, b = min(a + per, hi);
+    double s = 0.0;
+    int c = 0;
+    for (int i = a; i < b; ++i) { s += rate[i]; c += surf[i]; }
+    const double tot = block_sum(s, s_red);
+    int cw = c;
+    for (int o = 16; o > 0; o >>= 1) cw += __shfl_xor_sync(0xffffffffu, cw, o);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cw;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ct = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) ct += s_cnt[w];
+        bsum[blockIdx.x] = tot;
+        bcount[blockIdx.x] = ct;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_select_final(DevParams P, const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, int chunk,
+                                                       int nblocks, const double* __restrict__ bsum, const int* __restrict__ bcount, double u,
+                                                       long long* __restrict__ result, double* __restrict__ rtot) {
+    __shared__ double s_seg[1024];
+    __shared__ int s_segc[1024];
+    __shared__ double s_base;
+    __shared__ int s_blk, s_kbase;
+    __shared__ double s_r;
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int b = 0; b < nblocks; ++b) tot += bsum[b];
+        const double Rtot = P.Rd + tot;
+        const double r = u * Rtot;
+        rtot[0] = Rtot;
+        double run = 0.0;
+        int blk = -1, kb = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            if (run + bsum[b] > r) { blk = b; break; }
+            run += bsum[b];
+            kb += bcount[b];
+        }
+        s_blk = blk; s_base = run; s_kbase = kb; s_r = r;
+        if (blk < 0) { result[0] = -1; result[1] = -1; }
+    }
+    __syncthreads();
+    const int blk = s_blk;
+    if (blk < 0) return;
+    const int lo = blk * chunk, hi = min(lo + chunk, n);
+    const int per = (chunk + blockDim.x - 1) / blockDim.x;
+    const int a = lo + threadIdx.x * per, b = min(a + per, hi);
+    double s = 0.0;
+    int c = 0;
+    for (int i = a; i < b; ++i) { s += rate[i]; c += surf[i]; }
+    s_seg[threadIdx.x] = s;
+    s_segc[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = s_base;
+        int kb = s_kbase, seg = -1;
+        for (int t = 0; t < (int)blockDim.x; ++t) {
+            if (run + s_seg[t] > s_r) { seg = t; break; }
+            run += s_seg[t];
+            kb += s_segc[t];
+        }
+        long long found = -1, kfound = -1;
+        if (seg >= 0) {
+            const int a2 = lo + seg * per, b2 = min(a2 + per, hi);
+            for (int i = a2; i < b2; ++i) {
+                run += rate[i];
+                if (surf[i]) {
+                    if (run > s_r) { found = i; kfound = kb; break; }
+                    ++kb;
+                }
+            }
+        }
+        if (found < 0) {
+            // rounding left r between the chunk's bound and its re-associated sums: fall back to the last surface atom of the chunk
+            for (int i = hi - 1; i >= lo; --i)
+                if (surf[i]) { found = i; break; }
+            kfound = s_kbase;
+            for (int i = lo; i < found; ++i) kfound += surf[i];
+        }
+        result[0] = kfound;
+        result[1] = found;
+    }
+}
+
 // =============================================================================== misc
 
 // Periodic.py:22-25

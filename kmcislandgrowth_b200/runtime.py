@@ -327,6 +327,9 @@ class Context(object):
             check(rc)
         return st
 
+    def set_select_mode(self, mode):
+        check(self.lib.kmc_set_select_mode(self.handle, int(mode)))
+
     def set_relax_mode(self, mode):
         check(self.lib.kmc_set_relax_mode(self.handle, int(mode)))
 

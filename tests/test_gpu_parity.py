@@ -335,6 +335,32 @@ def test_fp32_vs_fp64_tolerance(name):
     assert worst[0][0] < 1e-9 and worst[0][1] < 1e-9       # fp64 is ~1e-13 in practice
 
 
+def test_block_scan_selection_matches_sequential_order():
+    """kmc_select's block-scan path (large tables) against the reference-order selection: identical index for
+    random u; a mismatch is only legal when r sits within rounding of a partial sum (none expected here)."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(64, 16, 16, aa_mode=1)
+    ctx = runtime.Context(runtime.params_from(gv), 0)
+    o = _oracle_for(gv)
+    rng = np.random.default_rng(5)
+    try:
+        for n in (1, 31, 1000, 70001, 300000):
+            surf = (rng.uniform(size=n) < 0.3).astype(np.uint8)
+            rate = np.where(surf > 0, 10.0 ** rng.uniform(0, 6, n), 0.0)
+            if n == 1000:
+                rate[surf > 0] *= 1e-9          # every hop far below Rd: mostly deposits
+            for mode in (1, 2):
+                ctx.set_select_mode(mode)
+                for u in np.concatenate([rng.uniform(size=12), [0.0, 1.0 - 2 ** -53]]):
+                    got = ctx.select(rate, surf, u)
+                    want = o.Select(rate, u)
+                    assert got[:2] == want[:2], (n, mode, u, got, want)
+                    assert abs(got[2] - want[2]) <= 1e-12 * want[2]
+        ctx.set_select_mode(0)
+    finally:
+        ctx.close()
+
+
 def test_edge_cases():
     """empty / single-atom inputs and atoms outside the cell grid"""
     from kmcislandgrowth_b200 import Bins, Energy, Growth, Periodic, runtime
