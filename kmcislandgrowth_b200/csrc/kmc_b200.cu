@@ -984,7 +984,17 @@ static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
     c->launches++;
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->timing) { cudaEventCreate(&ea); cudaEventCreate(&eb); cudaEventRecord(ea, c->stream); }
-    CK(cudaLaunchCooperativeKernel((const void*)k_relax2, dim3(blocks), dim3(R2_THREADS), args, 0, c->stream));
+    if (R.sync_mode == 0) {
+        CK(cudaLaunchCooperativeKernel((const void*)k_relax2, dim3(blocks), dim3(R2_THREADS), args, 0, c->stream));
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(R2_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = blocks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_relax2, R));
+    }
     if (c->timing) { cudaEventRecord(eb, c->stream); c->recs.push_back({family_id(c, "relax_persistent"), ea, eb}); }
     return 0;
 }
@@ -993,7 +1003,11 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
     KmcRelaxStats st{};
     const int n = (int)c->st_n;
     if (n == 0) { if (stats) *stats = st; return 0; }
-    const int blocks = std::min(c->sm_count, std::max(1, (n + 15) / 16));
+    // launch shape: one block (<= 16 adatoms), one cluster of <= 8 blocks (<= 256 adatoms), else one block per SM
+    int blocks = std::min(c->sm_count, std::max(1, (n + 15) / 16));
+    int sync_mode = 0;
+    if (blocks == 1) sync_mode = 1;
+    else if (n <= 256 && !getenv("KMC_NO_CLUSTER")) { blocks = std::min(blocks, 8); sync_mode = 2; }
     const int G = 0;
     if (c->item_cap == 0) c->item_cap = (size_t)n * 4 + (size_t)c->dp.ncell * 2 + 1024;
     for (int attempt = 0; attempt < 8; ++attempt) {
@@ -1030,8 +1044,9 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         R.stats = (KmcRelaxStatsDev*)(sync + 64);
         R.phase_ns = (unsigned long long*)(sync + 128);
         R.scale0 = scale0; R.threshold0 = threshold0; R.max_ls = max_ls;
+        R.sync_mode = sync_mode;
         R.debug = getenv("KMC_DEBUG_E") ? atoi(getenv("KMC_DEBUG_E")) : 0;
-        R.phase_block = getenv("KMC_PHASE_BLOCK") ? std::min(atoi(getenv("KMC_PHASE_BLOCK")), blocks - 1) : 0;
+        R.phase_block = !getenv("KMC_PHASE_TIMING") ? -1 : (getenv("KMC_PHASE_BLOCK") ? std::min(atoi(getenv("KMC_PHASE_BLOCK")), blocks - 1) : 0);
         TRY(launch_relax2(c, R, blocks));
         TRY(mail(c, sync, 256));
         const char* hm = (const char*)c->h_mail;

@@ -66,8 +66,24 @@ struct Relax2Args {
     KmcRelaxStatsDev* stats;
     unsigned long long* phase_ns;
     int phase_block;        // which block's thread 0 keeps the phase timers (diagnostics)
+    int sync_mode;          // 0: global atomic barrier (cooperative launch), 1: one block (__syncthreads), 2: one thread-block cluster (hardware barrier)
     int debug;              // diagnostics only: 1 = energy phase skips the pair arithmetic, 2 = skips the work items
 };
+
+// barrier between the phases of a line search, by launch shape:
+//  - many blocks: grid-wide barrier on a global counter (cooperative launch), ~2 us;
+//  - up to 8 blocks (small systems: the replica sweeps): ONE thread-block cluster, hardware barrier.cluster
+//    with release/acquire semantics (~0.2 us);
+//  - one block: __syncthreads (global writes of a block are visible to the block after it; L1 stays warm).
+__device__ __forceinline__ void relax2_barrier(const Relax2Args& R, unsigned int& epoch) {
+    if (R.sync_mode == 1) {
+        __syncthreads();
+    } else if (R.sync_mode == 2) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        grid_barrier(R.barrier, epoch);
+    }
+}
 
 struct Relax2Smem {
     int scan[R2_THREADS];
@@ -138,7 +154,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const DevParams& P = R.P;
     for (int c = gtid; c < R.ncell2; c += gthreads) R.start[c] = 0;
-    grid_barrier(R.barrier, epoch);
+    relax2_barrier(R, epoch);
     for (int k = gtid; k < R.n; k += gthreads) {
         int nx, ny;
         bin_index(P, src_pos[k].x, src_pos[k].y, nx, ny);
@@ -146,7 +162,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         R.key[k] = c;
         atomicAdd(&R.start[1 + c], 1);
     }
-    grid_barrier(R.barrier, epoch);
+    relax2_barrier(R, epoch);
     if (blockIdx.x == 0) {
         const int T = blockDim.x, t = threadIdx.x;
         const int m = R.ncell2 - 1;
@@ -167,12 +183,12 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         __syncthreads();
         for (int i = t; i < R.ncell2; i += T) R.cursor[i] = R.start[i];
     }
-    grid_barrier(R.barrier, epoch);
+    relax2_barrier(R, epoch);
     for (int k = gtid; k < R.n; k += gthreads) {
         const int slot = atomicAdd(&R.cursor[R.key[k]], 1);
         R.perm[slot] = k;
     }
-    grid_barrier(R.barrier, epoch);
+    relax2_barrier(R, epoch);
     // per cell: order by original index (deterministic), move the payload, count the work items
     for (int c = gtid; c < R.ncell2 - 1; c += gthreads) {
         const int lo = R.start[c], hi = R.start[c + 1];
@@ -209,7 +225,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         }
     }
     if (gtid == 0) R.chunks[0] = 0;
-    grid_barrier(R.barrier, epoch);
+    relax2_barrier(R, epoch);
     if (blockIdx.x == 0) {      // inclusive scan of chunks[1..ncell*PARTS]
         const int T = blockDim.x, t = threadIdx.x;
         const int m = P.ncell * R2_PARTS;
@@ -229,7 +245,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         for (int i = lo; i < hi; ++i) { run += R.chunks[i]; R.chunks[i] = run; }
         if (t == T - 1) *R.n_items = S.scan[t];      // true total; the caller checks it against item_cap
     }
-    grid_barrier(R.barrier, epoch);
+    relax2_barrier(R, epoch);
     for (int q = gtid; q < P.ncell * R2_PARTS; q += gthreads) {
         const int first = R.chunks[q], last = R.chunks[q + 1];
         if (first == last) continue;
@@ -249,7 +265,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
             R.items[k] = it;
         }
     }
-    grid_barrier(R.barrier, epoch);
+    relax2_barrier(R, epoch);
 }
 
 // ---- E: one work item ----------------------------------------------------------------------------
@@ -525,7 +541,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             R.partial[(size_t)threadIdx.x * nblk + blockIdx.x] = v;
         }
         PHASE2_MARK(0)
-        grid_barrier(R.barrier, epoch);
+        relax2_barrier(R, epoch);
         PHASE2_MARK(1)
         // ---------------- F
         const int nm = *R.n_movers;
@@ -535,7 +551,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane);
                 if (lane == 0) R.fix[w] = e;
             }
-            grid_barrier(R.barrier, epoch);
+            relax2_barrier(R, epoch);
             PHASE2_MARK(2)
         }
         // ---------------- S
@@ -579,7 +595,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             }
         }
         PHASE2_MARK(3)
-        grid_barrier(R.barrier, epoch);
+        relax2_barrier(R, epoch);
         PHASE2_MARK(4)
         // every block: beta and min-y from the same partials in the same order
         if (threadIdx.x < 32) {
@@ -605,7 +621,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         }
         relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S);
         PHASE2_MARK(5)
-        grid_barrier(R.barrier, epoch);
+        relax2_barrier(R, epoch);
         PHASE2_MARK(6)
         if (threadIdx.x < 32) {
             double mf = 0.0;
@@ -623,7 +639,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
         relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S);   // dx0, sn = dx0  :120,125
         first_pass = false;
-        grid_barrier(R.barrier, epoch);
+        relax2_barrier(R, epoch);
         line_search();                                                  // :121-129
         if (overflow) { status = -4; break; }
         maxF = S.ctl[3];

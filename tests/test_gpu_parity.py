@@ -335,6 +335,32 @@ def test_fp32_vs_fp64_tolerance(name):
     assert worst[0][0] < 1e-9 and worst[0][1] < 1e-9       # fp64 is ~1e-13 in practice
 
 
+@pytest.mark.parametrize("W,Hs,Ha,n,aa,cap", [(64, 16, 16, 1500, 1, 60), (48, 12, 10, 200, 0, 80), (18, 10, 10, 12, 0, 120)])
+def test_relaxation_engines_agree(W, Hs, Ha, n, aa, cap):
+    """The three Relaxation engines (host-driven launches, persistent kernel, persistent kernel on sorted state)
+    and all three launch shapes of the latter (one block, one cluster, cooperative grid) follow the same
+    trajectory: equal line-search / restart counts and positions to rounding; the oracle agrees as well."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(W, Hs, Ha, aa_mode=aa)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, n, seed=5 * W + n, sigma=0.05)
+    res = {}
+    for mode in (0, 1, 2):
+        ctx = runtime.Context(runtime.params_from(gv), 0)
+        ctx.set_relax_mode(mode)
+        sb = ctx.bins_create(sub)
+        ctx.state_set(ad)
+        st = ctx.relax(sb, 16, 1e-4, cap)
+        res[mode] = (ctx.state_get(), int(st.line_searches), int(st.restarts), st.maxF)
+        sb.close()
+        ctx.close()
+    o = _oracle_for(gv)
+    xo, sto, rc = o.Relaxation(ad, o.PutInBins(sub), max_line_searches=cap)
+    for mode in (0, 1, 2):
+        assert res[mode][1] == int(sto.line_searches) and res[mode][2] == int(sto.restarts), (mode, res[mode][1:], sto.line_searches)
+        assert np.max(np.abs(res[mode][0] - xo)) < 1e-7, mode
+    assert np.max(np.abs(res[2][0] - res[0][0])) < 1e-9 and np.max(np.abs(res[1][0] - res[0][0])) < 1e-9
+
+
 def test_block_scan_selection_matches_sequential_order():
     """kmc_select's block-scan path (large tables) against the reference-order selection: identical index for
     random u; a mismatch is only legal when r sits within rounding of a partial sum (none expected here)."""
