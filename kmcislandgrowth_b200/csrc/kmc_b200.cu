@@ -89,7 +89,7 @@ enum Slot {
     S_CELLOF, S_START, S_CURSOR, S_SXY, S_SIDX, S_PARTIAL, S_DONE, S_CAND, S_E, S_CTRL,
     S_F, S_FAA, S_FAS, S_X0, S_XN, S_XNP, S_SN, S_TMP0, S_TMP1, S_TMP2, S_TMP3,
     S_FLAG, S_MOVERS, S_NMOV, S_LPART, S_FIX, S_AMIN, S_RED, S_SYNC,
-    S_POS0, S_POS1, S_SD0, S_SD1, S_OI0, S_OI1, S_KEY, S_PERM, S_CHUNKS, S_ITEMS, S_COUNT
+    S_POS0, S_POS1, S_SD0, S_SD1, S_OI0, S_OI1, S_KEY, S_PERM, S_CHUNKS, S_ITEMS, S_NBR, S_COUNT
 };
 
 static int ensure(KmcCtx* c, DBuf& b, size_t bytes) {
@@ -1021,6 +1021,7 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         TRY(slot(c, S_OI0, (size_t)n, &R.oidx[0]));
         TRY(slot(c, S_OI1, (size_t)n, &R.oidx[1]));
         TRY(slot(c, S_CELLOF, (size_t)n, &R.cellof));
+        TRY(slot(c, S_NBR, (size_t)n * 4, &R.nbr));
         TRY(slot(c, S_FLAG, (size_t)n, &R.flag));
         TRY(slot(c, S_START, (size_t)R.ncell2, &R.start));
         TRY(slot(c, S_CURSOR, (size_t)R.ncell2, &R.cursor));
@@ -1060,6 +1061,7 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         if (getenv("KMC_PHASE_TIMING")) {
             const unsigned long long* ph = (const unsigned long long*)(hm + 128);
             const double nls = ds->line_searches > 0 ? (double)ds->line_searches : 1.0;
+            fprintf(stderr, "[kmc2 G detail us/ls] beta-reduce %.2f | rebuild-check %.2f\n", ph[10] / nls * 1e-3, ph[11] / nls * 1e-3);
             fprintf(stderr, "[kmc2 phase us/ls] E %.2f | bar %.2f | fix+bar %.2f | S %.2f | bar %.2f | G %.2f | bar %.2f | rebuild %.2f (%.1f us each, %lld) movers/ls %.1f (ls=%lld restarts=%lld blocks=%d G=%d items=%d)\n",
                     ph[0] / nls * 1e-3, ph[1] / nls * 1e-3, ph[2] / nls * 1e-3, ph[3] / nls * 1e-3, ph[4] / nls * 1e-3, ph[5] / nls * 1e-3,
                     ph[6] / nls * 1e-3, ph[7] / nls * 1e-3, ph[8] ? ph[7] * 1e-3 / ph[8] : 0.0, (long long)ph[8], ph[9] / nls, (long long)ds->line_searches, (long long)ds->restarts, blocks, G, *(const int*)(hm + 20));

@@ -43,6 +43,8 @@ struct Relax2Args {
     double2* sdir[2];       // sorted: search direction (ping-pong across rebuilds)
     int* oidx[2];           // sorted: original index
     int* cellof;            // sorted: cell of the slot in the current cell list
+    int4* nbr;              // sorted, 4 x int4 per slot: adatom partner ranges b[4], e[4], substrate ranges b[4], e[4] of the
+                            // slot's stencil columns (valid until the next rebuild; b[0] = -1: use the generic stencil walk)
     uint8_t* flag;          // sorted: 1 = mover on the current line
     int* start;             // [ncell+2]
     int* cursor;            // [ncell+2]
@@ -210,6 +212,30 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
             dst_s[s] = src_s ? src_s[k] : make_double2(0.0, 0.0);
             dst_oidx[s] = src_oidx ? src_oidx[k] : k;
             R.cellof[s] = c;
+        }
+        if (hi > lo) {      // stencil ranges of this cell's atoms: one dependent fetch less in every force sweep
+            int4 ab = make_int4(-1, 0, 0, 0), ae = make_int4(0, 0, 0, 0), sb = ab, se = ae;
+            if (c < P.ncell) {
+                const Stencil st = cell_stencil(P, c / P.nby, c % P.nby);
+                const bool ycontig = (st.ys[0] >= 0) && (st.ys[2] < P.nby) && (st.ys[1] == st.ys[0] + 1) && (st.ys[2] == st.ys[1] + 1);
+                if (ycontig) {
+                    int b1[4], e1[4], b2[4], e2[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int cx = st.xs[a];
+                        const bool ok = a < st.nxs && cx >= 0 && cx < P.nbx;
+                        b1[a] = ok ? R.start[cx * P.nby + st.ys[0]] : 0;
+                        e1[a] = ok ? R.start[cx * P.nby + st.ys[2] + 1] : 0;
+                        b2[a] = ok ? R.sub.start[cx * P.nby + st.ys[0]] : 0;
+                        e2[a] = ok ? R.sub.start[cx * P.nby + st.ys[2] + 1] : 0;
+                    }
+                    ab = make_int4(b1[0], b1[1], b1[2], b1[3]); ae = make_int4(e1[0], e1[1], e1[2], e1[3]);
+                    sb = make_int4(b2[0], b2[1], b2[2], b2[3]); se = make_int4(e2[0], e2[1], e2[2], e2[3]);
+                }
+            }
+            for (int s2 = lo; s2 < hi; ++s2) {
+                R.nbr[4 * s2] = ab; R.nbr[4 * s2 + 1] = ae; R.nbr[4 * s2 + 2] = sb; R.nbr[4 * s2 + 3] = se;
+            }
         }
         if (c < P.ncell) {
             const int nh = hi - lo;
@@ -382,6 +408,27 @@ __device__ __forceinline__ void stencil_forces(const DevParams& P, const CellVie
     }
 }
 
+// forces of up to four contiguous slot ranges (the stencil columns, in stencil order) on (xi, yi): the ranges are
+// walked as ONE flat index space and eight neighbour positions are fetched before their arithmetic, so a sweep
+// costs one or two L2 round trips instead of one per column (after a grid barrier every first touch misses L1;
+// a dependent L2 access measures ~0.45 us here)
+__device__ __forceinline__ void flat_forces(const DevParams& P, const double2* ptr, int4 b, int4 e, int lane, int G, double xi, double yi,
+                                            double E, double r0sq, double& fx, double& fy, unsigned long long& visits) {
+    const int c0 = e.x - b.x, c1 = c0 + (e.y - b.y), c2 = c1 + (e.z - b.z), tot = c2 + (e.w - b.w);
+    for (int t = lane; t < tot; t += 8 * G) {
+        double2 p[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int tk = min(t + k * G, tot - 1);
+            const int sl = tk < c0 ? b.x + tk : (tk < c1 ? b.y + (tk - c0) : (tk < c2 ? b.z + (tk - c1) : b.w + (tk - c2)));
+            p[k] = ptr[sl];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (t + k * G < tot) { acc_force(P, xi, yi, p[k], E, r0sq, fx, fy); ++visits; }
+    }
+}
+
 __device__ __forceinline__ double group_sum_rt(double v, int G) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -412,13 +459,23 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
         double2 pi = make_double2(0, 0);
         if (live) {
             pi = pos[slot];
-            const Stencil st = make_stencil(P, pi.x, pi.y);
-            if (P.aa_mode == 0) {
-                for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
-            } else {
-                if (R.debug != 3) stencil_forces(P, ad, st, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
+            const int4 ab = R.nbr[4 * slot], ae = R.nbr[4 * slot + 1], sb = R.nbr[4 * slot + 2], se = R.nbr[4 * slot + 3];
+            if (ab.x >= 0) {        // stencil ranges cached at the last rebuild
+                if (P.aa_mode == 0) {
+                    for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
+                } else {
+                    flat_forces(P, pos, ab, ae, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
+                }
+                flat_forces(P, R.sub.sxy, sb, se, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
+            } else {                // atoms outside the grid / y-wrapped stencils: generic walk from the raw position
+                const Stencil st = make_stencil(P, pi.x, pi.y);
+                if (P.aa_mode == 0) {
+                    for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
+                } else {
+                    stencil_forces(P, ad, st, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
+                }
+                stencil_forces(P, R.sub, st, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
             }
-            if (R.debug != 3 && R.debug != 5) stencil_forces(P, R.sub, st, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
         }
         ax = group_sum_rt(ax, G); ay = group_sum_rt(ay, G);
         sx = group_sum_rt(sx, G); sy = group_sum_rt(sy, G);
@@ -609,6 +666,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         }
         __syncthreads();
         const double beta = S.ctl[0] / S.ctl[1];                          // :143-145
+        PHASE2_MARK(10)
         // ---------------- rebuild (rare) + G
         if (*R.need_rebuild) {
             relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S);
@@ -619,6 +677,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             cs ^= 1;          // the rebuilt x_np now lives in pos[cur]: make it the "next" buffer by flipping cur
             cur ^= 1;
         }
+        PHASE2_MARK(11)
         relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S);
         PHASE2_MARK(5)
         relax2_barrier(R, epoch);
