@@ -62,8 +62,8 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
         const unsigned int target = (epoch + 1u) * gridDim.x;
         atomicAdd(bar, 1u);
         unsigned int v;
-        do {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        do {            // poll in L2 (volatile load: no L1 invalidation per iteration); the fence below is the acquire
+            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < target);
         __threadfence();
     }

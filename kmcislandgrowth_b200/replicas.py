@@ -50,10 +50,20 @@ def run_replica_gpu(r, grid, n_events, device, max_line_searches=0, W=18, Hs=10,
             "mean_height": float(ad[1::2].mean()) if ad.size else 0.0}
 
 
-def run_sweep(grid, n_events, runner=run_replica_gpu, world_size=1, rank=0, device=0, gather=None, **kw):
+def run_sweep(grid, n_events, runner=run_replica_gpu, world_size=1, rank=0, device=0, gather=None, threads=1, **kw):
     """Run this rank's share of the sweep; `gather(local_list) -> list of all ranks' lists` joins the
-    summaries (None: single process).  Returns the summaries of ALL replicas, ordered by replica id."""
-    mine = [runner(r, grid, n_events, device, **kw) for r in assign(len(grid), world_size, rank)]
+    summaries (None: single process).  Returns the summaries of ALL replicas, ordered by replica id.
+
+    threads > 1 runs that many replicas of this rank CONCURRENTLY on its GPU: every replica owns a context and
+    a stream, its relaxations are single-block or single-cluster launches (<= 8 SMs), so several fit on the 148
+    SMs at once; the ctypes calls release the GIL while they wait."""
+    ids = assign(len(grid), world_size, rank)
+    if threads > 1 and len(ids) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            mine = list(ex.map(lambda r: runner(r, grid, n_events, device, **kw), ids))
+    else:
+        mine = [runner(r, grid, n_events, device, **kw) for r in ids]
     if gather is None:
         allr = [mine]
     else:
