@@ -133,6 +133,30 @@ def HopAtom(i, adatoms, substrate_bins, u=None, max_line_searches=0, stats=None)
     return ctx.state_get()
 
 
+def IslandStatistics(adatoms, gv=None):
+    """Islands = connected components of the adatoms under the reference's bond rule d < 1.2 r_a with the
+    x-periodic minimum image (Bins.py:100, Periodic.py:27-36).  Analysis helper (host side, not on the hot path):
+    -> dict(n_islands, sizes (descending), density per unit length, largest)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    gv = _gv() if gv is None else gv
+    ad = np.asarray(adatoms, dtype=np.float64).reshape(-1, 2)
+    n = ad.shape[0]
+    if n == 0:
+        return {"n_islands": 0, "sizes": [], "density": 0.0, "largest": 0}
+    pts = ad.copy()
+    pts[:, 0] = np.mod(pts[:, 0] + gv.L / 2, gv.L)
+    span = float(pts[:, 1].max() - pts[:, 1].min()) + 10 * gv.r_a
+    pts[:, 1] -= pts[:, 1].min()
+    tree = cKDTree(pts, boxsize=[gv.L, max(span, 4 * gv.r_a) * 4])
+    pairs = tree.query_pairs(1.2 * gv.r_a, output_type="ndarray")
+    g = coo_matrix((np.ones(len(pairs)), (pairs[:, 0], pairs[:, 1])), shape=(n, n)) if len(pairs) else coo_matrix((n, n))
+    ncomp, lab = connected_components(g, directed=False)
+    sizes = sorted(np.bincount(lab).tolist(), reverse=True)
+    return {"n_islands": int(ncomp), "sizes": sizes, "density": ncomp / float(gv.L), "largest": int(sizes[0])}
+
+
 class Simulation(object):
     """The KMC loop of 2DGrowth.py:305-329 on a device-resident trajectory.
 
@@ -149,6 +173,7 @@ class Simulation(object):
         self.sbins = self.ctx.bins_create(sub)
         self.ctx.state_set(np.zeros(0) if adatoms is None else np.asarray(adatoms, dtype=np.float64))
         self.t = 0
+        self.time = 0.0          # physical KMC clock (extension: the reference only counts events, 2DGrowth.py:316,343)
         self.log = []
 
     @property
@@ -158,15 +183,35 @@ class Simulation(object):
     def set_adatoms(self, adatoms):
         self.ctx.state_set(np.asarray(adatoms, dtype=np.float64))
 
-    def step(self, u0=None, u1=None, max_line_searches=0):
+    def step(self, u0=None, u1=None, max_line_searches=0, u_clock=None):
+        """one event; with u_clock in (0, 1] the residence time dt = -ln(u_clock)/Rtot is added to self.time"""
         u0 = random.random() if u0 is None else u0
         u1 = random.random() if u1 is None else u1
         kind, hk, rtot, st = self.ctx.event(self.sbins, u0, u1, max_line_searches)
         self.t += 1
+        if u_clock is not None and rtot > 0:
+            self.time += -np.log(u_clock) / rtot
         rec = dict(t=self.t, kind=kind, hop_k=hk, rtot=rtot, line_searches=st.line_searches, restarts=st.restarts,
                    maxF=st.maxF, status=st.status)
         self.log.append(rec)
         return rec
+
+    def save(self, path):
+        """checkpoint: positions, substrate, constants, counters (npz)"""
+        p = self.params
+        np.savez_compressed(path, adatoms=self.adatoms, substrate=self.substrate, t=self.t, time=self.time,
+                            params=np.array([getattr(p, f) for f, _ in p._fields_], dtype=np.float64))
+
+    @classmethod
+    def load(cls, path, device=None):
+        from ._lib import KmcParams
+        z = np.load(path)
+        p = KmcParams()
+        for (f, ct), v in zip(p._fields_, z["params"]):
+            setattr(p, f, int(v) if "int" in ct.__name__ else float(v))
+        sim = cls(adatoms=z["adatoms"], substrate=z["substrate"], device=device, params=p)
+        sim.t, sim.time = int(z["t"]), float(z["time"])
+        return sim
 
     def close(self):
         self.sbins.close()

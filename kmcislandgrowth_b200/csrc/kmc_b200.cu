@@ -220,7 +220,16 @@ static int build_cells(KmcCtx* c, const double2* d_xy, int n, int B, int* cell_o
         dim3 g(std::min(cdiv(n, 256), 1024u), B);
         LAUNCH(c, "bin_count", k_bin_count, g, 256, c->dp, d_xy, n, B, cell_of, start);
     }
-    LAUNCH(c, "bin_scan", k_bin_scan, B, 1024, ncell2, start, cursor);
+    if (B == 1 && ncell2 > 16384) {      // whole-device tiled scan for large grids
+        const int m = ncell2 - 1;
+        const int tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+        int* tile_tot;
+        TRY(slot(c, S_AMIN, (size_t)tiles, &tile_tot));
+        LAUNCH(c, "bin_scan", k_bin_scan_tiles, tiles, 1024, m, start, tile_tot);
+        LAUNCH(c, "bin_scan", k_bin_scan_add, tiles, 1024, m, start, tile_tot, cursor);
+    } else {
+        LAUNCH(c, "bin_scan", k_bin_scan, B, 1024, ncell2, start, cursor);
+    }
     if (n > 0) {
         dim3 g(std::min(cdiv(n, 256), 1024u), B);
         LAUNCH(c, "bin_scatter", k_bin_scatter, g, 256, n, B, ncell2, cell_of, cursor, sidx);

@@ -68,6 +68,48 @@ __global__ void k_bin_scan(int ncell2 /* ncell+2 */, int* __restrict__ start, in
     for (int i = threadIdx.x; i < ncell2; i += blockDim.x) cur[i] = a[i];
 }
 
+// Large grids (one configuration, > 16k cells): tiled scan over the whole device instead of one block.
+// Pass 1: every block scans its tile of SCAN_TILE entries of a[1..m] in place (inclusive) and stores the tile total.
+// Pass 2: every block adds the sum of the totals of the tiles before it, and mirrors the result into `cursor`.
+constexpr int SCAN_TILE = 8192;
+__global__ void __launch_bounds__(1024) k_bin_scan_tiles(int m, int* __restrict__ a /* entries 1..m */, int* __restrict__ tile_tot) {
+    __shared__ int s_tot[1024];
+    const int per = SCAN_TILE / 1024;
+    const int lo = 1 + blockIdx.x * SCAN_TILE + threadIdx.x * per;
+    int v[SCAN_TILE / 1024];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < per; ++k) { v[k] = (lo + k <= m) ? a[lo + k] : 0; sum += v[k]; }
+    s_tot[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int t = (threadIdx.x >= off) ? s_tot[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_tot[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int run = s_tot[threadIdx.x] - sum;
+#pragma unroll
+    for (int k = 0; k < per; ++k) { run += v[k]; if (lo + k <= m) a[lo + k] = run; }
+    if (threadIdx.x == 1023) tile_tot[blockIdx.x] = s_tot[1023];
+}
+
+__global__ void __launch_bounds__(1024) k_bin_scan_add(int m, int* __restrict__ a, const int* __restrict__ tile_tot, int* __restrict__ cursor) {
+    __shared__ int s_red[32];
+    __shared__ int s_base;
+    int part = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += 1024) part += tile_tot[t];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) { int b = 0; for (int w = 0; w < 32; ++w) b += s_red[w]; s_base = b; }
+    __syncthreads();
+    const int base = s_base;
+    const int lo = 1 + blockIdx.x * SCAN_TILE;
+    for (int i = lo + threadIdx.x; i < lo + SCAN_TILE && i <= m; i += 1024) { const int v = a[i] + base; a[i] = v; cursor[i] = v; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cursor[0] = a[0];
+}
+
 // slot = cursor[cell]++ ; sidx[slot] = i   (order inside a cell fixed up by k_bin_order)
 __global__ void k_bin_scatter(int n, int B, int ncell2, const int* __restrict__ cell_of, int* __restrict__ cursor,
                               int* __restrict__ sidx) {

@@ -105,3 +105,37 @@ def test_oracle_bins3x3_mode_consistency():
         assert k == want
         if k >= 0:
             assert dense == np.nonzero(surf)[0][k]
+
+
+def test_island_statistics_against_brute_force():
+    """Growth.IslandStatistics: connected components under d < 1.2 r_a with the x-periodic minimum image."""
+    from kmcislandgrowth_b200 import Growth, workloads
+    gv = workloads.constants_for(48, 12, 10)
+    ad = workloads.film(gv, 150, seed=3, sigma=0.05)
+    got = Growth.IslandStatistics(ad, gv)
+    o = orc.Oracle(orc.make_params(W=48, Hs=12, Ha=10))
+    d = o.Distances(ad, ad)
+    n = ad.size // 2
+    adj = d < 1.2 * gv.r_a
+    lab = -np.ones(n, dtype=int)
+    comp = 0
+    for i in range(n):
+        if lab[i] >= 0:
+            continue
+        stack = [i]
+        lab[i] = comp
+        while stack:
+            k = stack.pop()
+            for j in np.nonzero(adj[k])[0]:
+                if lab[j] < 0:
+                    lab[j] = comp
+                    stack.append(j)
+        comp += 1
+    assert got["n_islands"] == comp
+    assert got["sizes"] == sorted(np.bincount(lab).tolist(), reverse=True)
+    # the golden trajectory of the reference: island statistics per event are reproducible observables
+    z = np.load(os.path.join(GOLDEN, "trajectory.npz"))
+    offs, vals = z["states_offs"], z["states_vals"]
+    g18 = workloads.constants_for(18)
+    last = Growth.IslandStatistics(vals[offs[-2]:offs[-1]], g18)
+    assert last["n_islands"] >= 1 and sum(last["sizes"]) == (offs[-1] - offs[-2]) // 2

@@ -361,6 +361,33 @@ def test_relaxation_engines_agree(W, Hs, Ha, n, aa, cap):
     assert np.max(np.abs(res[2][0] - res[0][0])) < 1e-9 and np.max(np.abs(res[1][0] - res[0][0])) < 1e-9
 
 
+def test_checkpoint_and_island_statistics(tmp_path):
+    """Simulation.save / load round trip, the KMC clock extension, and island statistics of a GPU trajectory equal to
+    those of the reference's trajectory (same uniforms -> same states -> same observables)."""
+    from kmcislandgrowth_b200 import Growth, workloads
+    z = np.load(os.path.join(GOLDEN, "trajectory.npz"))
+    us, offs, vals = z["uniforms"], z["states_offs"], z["states_vals"]
+    sim = Growth.Simulation()
+    pos = 0
+    for t in range(8):
+        sim.step(us[pos], us[pos + 1], u_clock=0.5)
+        pos = int(z["uniforms_used"][t])
+    assert sim.time > 0
+    gv = workloads.constants_for(18)
+    ref_state = vals[offs[7]:offs[8]]
+    assert np.max(np.abs(sim.adatoms - ref_state)) < 1e-5
+    assert Growth.IslandStatistics(sim.adatoms, gv) == Growth.IslandStatistics(ref_state, gv)
+    path = str(tmp_path / "ckpt.npz")
+    sim.save(path)
+    sim2 = Growth.Simulation.load(path)
+    assert np.array_equal(sim2.adatoms, sim.adatoms) and sim2.t == 8 and sim2.time == sim.time
+    a = sim.step(us[pos], us[pos + 1])
+    b = sim2.step(us[pos], us[pos + 1])
+    assert a["kind"] == b["kind"] and a["line_searches"] == b["line_searches"] and np.array_equal(sim.adatoms, sim2.adatoms)
+    sim.close()
+    sim2.close()
+
+
 def test_block_scan_selection_matches_sequential_order():
     """kmc_select's block-scan path (large tables) against the reference-order selection: identical index for
     random u; a mismatch is only legal when r sits within rounding of a partial sum (none expected here)."""
