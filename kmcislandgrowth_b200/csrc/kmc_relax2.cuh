@@ -191,28 +191,52 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         R.perm[slot] = k;
     }
     relax2_barrier(R, epoch);
-    // per cell: order by original index (deterministic), move the payload, count the work items
-    for (int c = gtid; c < R.ncell2 - 1; c += gthreads) {
+    // per cell: order by original index (deterministic), move the payload, count the work items.
+    // One WARP per cell: cells of up to 32 atoms are ranked with shuffles (three dependent fetches in all); the
+    // rest of the per-cell work below is done by lane 0.
+    const int gwarp_ = gtid >> 5, nwarps_ = gthreads >> 5, lane_ = threadIdx.x & 31;
+    for (int c = gwarp_; c < R.ncell2 - 1; c += nwarps_) {
         const int lo = R.start[c], hi = R.start[c + 1];
-        for (int i = lo + 1; i < hi; ++i) {          // insertion sort of perm[lo..hi) keyed on the original index
-            const int v = R.perm[i];
-            const int kv = src_oidx ? src_oidx[v] : v;
-            int j = i - 1;
-            while (j >= lo) {
-                const int w = R.perm[j];
-                if ((src_oidx ? src_oidx[w] : w) <= kv) break;
-                R.perm[j + 1] = w;
-                --j;
+        const int m = hi - lo;
+        if (m == 0) {               // empty cell: no work items (the counters still have to be defined)
+            if (lane_ < R2_PARTS && c < P.ncell) R.chunks[c * R2_PARTS + lane_] = 0;
+            if (lane_ == 0 && c < P.ncell) R.cursor[1 + c] = 0;
+            continue;
+        }
+        if (m <= 32) {
+            int k = 0, key = 0x7fffffff;
+            if (lane_ < m) { k = R.perm[lo + lane_]; key = src_oidx ? src_oidx[k] : k; }
+            int rank = 0;
+            for (int j = 0; j < m; ++j) rank += (__shfl_sync(0xffffffffu, key, j) < key);
+            if (lane_ < m) {
+                const int s = lo + rank;
+                dst_pos[s] = src_pos[k];
+                dst_s[s] = src_s ? src_s[k] : make_double2(0.0, 0.0);
+                dst_oidx[s] = key;
+                R.cellof[s] = c;
             }
-            R.perm[j + 1] = v;
+        } else if (lane_ == 0) {
+            for (int i = lo + 1; i < hi; ++i) {          // insertion sort of perm[lo..hi) keyed on the original index
+                const int v = R.perm[i];
+                const int kv = src_oidx ? src_oidx[v] : v;
+                int j = i - 1;
+                while (j >= lo) {
+                    const int w = R.perm[j];
+                    if ((src_oidx ? src_oidx[w] : w) <= kv) break;
+                    R.perm[j + 1] = w;
+                    --j;
+                }
+                R.perm[j + 1] = v;
+            }
+            for (int s = lo; s < hi; ++s) {
+                const int k = R.perm[s];
+                dst_pos[s] = src_pos[k];
+                dst_s[s] = src_s ? src_s[k] : make_double2(0.0, 0.0);
+                dst_oidx[s] = src_oidx ? src_oidx[k] : k;
+                R.cellof[s] = c;
+            }
         }
-        for (int s = lo; s < hi; ++s) {
-            const int k = R.perm[s];
-            dst_pos[s] = src_pos[k];
-            dst_s[s] = src_s ? src_s[k] : make_double2(0.0, 0.0);
-            dst_oidx[s] = src_oidx ? src_oidx[k] : k;
-            R.cellof[s] = c;
-        }
+        if (lane_ != 0) continue;
         if (hi > lo) {      // stencil ranges of this cell's atoms: one dependent fetch less in every force sweep
             int4 ab = make_int4(-1, 0, 0, 0), ae = make_int4(0, 0, 0, 0), sb = ab, se = ae;
             if (c < P.ncell) {
@@ -239,6 +263,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         }
         if (c < P.ncell) {
             const int nh = hi - lo;
+            int tot = 0;
 #pragma unroll
             for (int part = 0; part < R2_PARTS; ++part) {
                 int cnt = 0;
@@ -246,19 +271,21 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
                     const Ranges r = partner_ranges(P, R.start, R.sub.start, c, part);
                     cnt = (nh * r.total + R2_CHUNK - 1) / R2_CHUNK;
                 }
-                R.chunks[1 + c * R2_PARTS + part] = cnt;
+                R.chunks[c * R2_PARTS + part] = cnt;
+                tot += cnt;
             }
+            R.cursor[1 + c] = tot;          // items of this home cell (the scatter cursor is free again)
         }
     }
-    if (gtid == 0) R.chunks[0] = 0;
+    if (gtid == 0) R.cursor[0] = 0;
     relax2_barrier(R, epoch);
-    if (blockIdx.x == 0) {      // inclusive scan of chunks[1..ncell*PARTS]
+    if (blockIdx.x == 0) {      // inclusive scan of the per-cell item counts cursor[1..ncell]
         const int T = blockDim.x, t = threadIdx.x;
-        const int m = P.ncell * R2_PARTS;
+        const int m = P.ncell;
         const int per = (m + T - 1) / T;
         const int lo = 1 + t * per, hi = min(lo + per, m + 1);
         int sum = 0;
-        for (int i = lo; i < hi; ++i) sum += R.chunks[i];
+        for (int i = lo; i < hi; ++i) sum += R.cursor[i];
         S.scan[t] = sum;
         __syncthreads();
         for (int off = 1; off < T; off <<= 1) {
@@ -268,27 +295,32 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
             __syncthreads();
         }
         int run = S.scan[t] - sum;
-        for (int i = lo; i < hi; ++i) { run += R.chunks[i]; R.chunks[i] = run; }
+        for (int i = lo; i < hi; ++i) { run += R.cursor[i]; R.cursor[i] = run; }
         if (t == T - 1) *R.n_items = S.scan[t];      // true total; the caller checks it against item_cap
     }
     relax2_barrier(R, epoch);
-    for (int q = gtid; q < P.ncell * R2_PARTS; q += gthreads) {
-        const int first = R.chunks[q], last = R.chunks[q + 1];
-        if (first == last) continue;
-        const int c = q / R2_PARTS, part = q % R2_PARTS;
+    for (int c = gtid; c < P.ncell; c += gthreads) {
+        int k = R.cursor[c];
+        const int kend = R.cursor[c + 1];
+        if (k == kend) continue;
         const int nh = R.start[c + 1] - R.start[c];
-        const Ranges r = partner_ranges(P, R.start, R.sub.start, c, part);
-        const int pairs = nh * r.total;
-        WorkItem it;
-        it.hb = R.start[c]; it.nh = nh;
-        it.b0 = r.b[0]; it.n0 = r.e[0] - r.b[0]; it.b1 = r.b[1]; it.n1 = r.e[1] - r.b[1]; it.b2 = r.b[2];
-        it.kind = r.self[0] | (r.self[1] << 1) | (r.self[2] << 2) | (part >= 4 ? 8 : 0);
-        it.inv_nh = 1.0f / (float)nh;
-        it.pad = 0;
-        for (int k = first; k < last && k < R.item_cap; ++k) {
-            it.begin = (k - first) * R2_CHUNK;
-            it.count = min(R2_CHUNK, pairs - it.begin);
-            R.items[k] = it;
+        for (int part = 0; part < R2_PARTS; ++part) {
+            const int cnt = R.chunks[c * R2_PARTS + part];
+            if (cnt == 0) continue;
+            const Ranges r = partner_ranges(P, R.start, R.sub.start, c, part);
+            const int pairs = nh * r.total;
+            WorkItem it;
+            it.hb = R.start[c]; it.nh = nh;
+            it.b0 = r.b[0]; it.n0 = r.e[0] - r.b[0]; it.b1 = r.b[1]; it.n1 = r.e[1] - r.b[1]; it.b2 = r.b[2];
+            it.kind = r.self[0] | (r.self[1] << 1) | (r.self[2] << 2) | (part >= 4 ? 8 : 0);
+            it.inv_nh = 1.0f / (float)nh;
+            it.pad = 0;
+            for (int j = 0; j < cnt; ++j, ++k) {
+                if (k >= R.item_cap) break;
+                it.begin = j * R2_CHUNK;
+                it.count = min(R2_CHUNK, pairs - it.begin);
+                R.items[k] = it;
+            }
         }
     }
     relax2_barrier(R, epoch);
