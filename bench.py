@@ -329,7 +329,12 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_relax2 (persistent: one launch = one Relaxation; per line search 20 candidate energies + 1 force sweep)",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": abytes, "bytes_detail": binfo,
+                         "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of k_relax2 from the committed ncu --set full capture
+                         # (profiles/r1d_relax2_ncu.md, revision g: 0.852 MB for a 200-line-search launch), scaled to this run's
+                         # line searches per launch: the working set is L2 resident, DRAM sees first touches only
+                         "traffic": 852224.0 / 200.0 * ls_mean, "traffic_source": "profiles/r1d_relax2_ncu.md (4.26 kB per line search)",
+                         "algorithmic_bytes_per_launch": abytes, "bytes_detail": binfo,
                          "avg_launch_us": k_ms * 1e3, "launches": ek["launches"],
                          "kernel_share_of_gpu_time": ek["ms"] / total_kernel_ms if total_kernel_ms else None,
                          "binding_roof": "fp64 pipe (about 80 flop per algorithmic byte, SURVEY.md §8d)",
