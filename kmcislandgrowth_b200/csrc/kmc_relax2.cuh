@@ -470,7 +470,13 @@ __device__ __forceinline__ double group_sum_rt(double v, int G) {
 // processed in rounds; each round gives every atom G lanes, G = the largest power of two that lets the round
 // cover at least half of what is left (64 atoms x 8 lanes, then 4 atoms x 32 lanes for 68 atoms on 512 threads).
 __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2* pos, double2* sdir, const int* oidx, int mode, double beta,
-                                              double scale, bool count_pairs, Relax2Smem& S) {
+                                              double scale, bool count_pairs, Relax2Smem& S, unsigned long long* tm = nullptr) {
+#define GMARK(k)                                                                          \
+    if (tm && threadIdx.x == 0 && blockIdx.x == R.phase_block) {                          \
+        const unsigned long long _t = gtimer();                                           \
+        R.phase_ns[k] += _t - *tm;                                                        \
+        *tm = _t;                                                                         \
+    }
     const DevParams& P = R.P;
     const int T = blockDim.x;
     const int per = (R.n + gridDim.x - 1) / gridDim.x;
@@ -488,9 +494,10 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
         const int slot = r0 + threadIdx.x / G;
         const bool live = slot < hi;
         double ax = 0, ay = 0, sx = 0, sy = 0;
-        double2 pi = make_double2(0, 0);
+        double2 pi = make_double2(0, 0), so = make_double2(0, 0);
         if (live) {
             pi = pos[slot];
+            if (lane == 0 && mode == 1) so = sdir[slot];       // fetched together with the position, used by the fused update
             const int4 ab = R.nbr[4 * slot], ae = R.nbr[4 * slot + 1], sb = R.nbr[4 * slot + 2], se = R.nbr[4 * slot + 3];
             if (ab.x >= 0) {        // stencil ranges cached at the last rebuild
                 if (P.aa_mode == 0) {
@@ -498,7 +505,9 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
                 } else {
                     flat_forces(P, pos, ab, ae, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
                 }
+                GMARK(12)
                 flat_forces(P, R.sub.sxy, sb, se, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
+                GMARK(13)
             } else {                // atoms outside the grid / y-wrapped stencils: generic walk from the raw position
                 const Stencil st = make_stencil(P, pi.x, pi.y);
                 if (P.aa_mode == 0) {
@@ -511,6 +520,7 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
         }
         ax = group_sum_rt(ax, G); ay = group_sum_rt(ay, G);
         sx = group_sum_rt(sx, G); sy = group_sum_rt(sy, G);
+        GMARK(14)
         if (live && lane == 0) {
             const double fx = ax + sx, fy = ay + sy;                // 2DGrowth.py:120
             double2 sn;
@@ -518,12 +528,12 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
                 sn = make_double2(fx, fy);
             } else {
                 mf = fmax(mf, fx * fx + fy * fy);                   // :129,160
-                const double2 so = sdir[slot];
                 sn = make_double2(__dadd_rn(fx, __dmul_rn(beta, so.x)), __dadd_rn(fy, __dmul_rn(beta, so.y)));   // :147
             }
             sdir[slot] = sn;
             R.flag[slot] = (R.debug == 4) ? 0 : mover_flag(P, pi, sn, scale);
         }
+        GMARK(15)
         r0 += groups;
     }
     if (mode == 1) {
@@ -710,7 +720,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             cur ^= 1;
         }
         PHASE2_MARK(11)
-        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S);
+        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, &t_mark);
         PHASE2_MARK(5)
         relax2_barrier(R, epoch);
         PHASE2_MARK(6)
