@@ -87,7 +87,12 @@ __device__ __forceinline__ void relax2_barrier(const Relax2Args& R, unsigned int
     }
 }
 
+constexpr int R2_STAGE = 1024;       // atoms of the neighbourhood staged in shared memory by the force phase (16 KB)
+
 struct Relax2Smem {
+    alignas(16) double2 stage[R2_STAGE];     // positions of slots [smin, smax): one TMA 1-D bulk copy per block and line search
+    alignas(8) unsigned long long mbar;      // mbarrier the bulk copy completes on
+    int smin, smax;
     int scan[R2_THREADS];
     double wred[R2_THREADS / 32][KC];
     double e[KC];
@@ -440,6 +445,29 @@ __device__ __forceinline__ void stencil_forces(const DevParams& P, const CellVie
     }
 }
 
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous slot range into shared memory ----------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // forces of up to four contiguous slot ranges (the stencil columns, in stencil order) on (xi, yi): the ranges are
 // walked as ONE flat index space and eight neighbour positions are fetched before their arithmetic, so a sweep
 // costs one or two L2 round trips instead of one per column (after a grid barrier every first touch misses L1;
@@ -461,6 +489,33 @@ __device__ __forceinline__ void flat_forces(const DevParams& P, const double2* p
     }
 }
 
+// Slot range covered by the stencils of this block's chunk of atoms.  The atoms are cell-sorted column-major and only
+// a few cells of a column are occupied, so the stencils of a contiguous chunk cover ONE contiguous slot range (three
+// adjacent columns) except at the periodic seam.  Valid until the next rebuild.
+__device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Smem& S, int& smin, int& smax) {
+    const int T = blockDim.x;
+    const int per = (R.n + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+    __syncthreads();
+    if (threadIdx.x == 0) { S.smin = 0x7fffffff; S.smax = -1; }
+    __syncthreads();
+    if (R.P.aa_mode != 0) {
+        for (int slot = lo + threadIdx.x; slot < hi; slot += T) {
+            const int4 ab = R.nbr[4 * slot], ae = R.nbr[4 * slot + 1];
+            if (ab.x < 0) continue;
+            int mn = 0x7fffffff, mx = -1;
+            if (ae.x > ab.x) { mn = min(mn, ab.x); mx = max(mx, ae.x); }
+            if (ae.y > ab.y) { mn = min(mn, ab.y); mx = max(mx, ae.y); }
+            if (ae.z > ab.z) { mn = min(mn, ab.z); mx = max(mx, ae.z); }
+            if (ae.w > ab.w) { mn = min(mn, ab.w); mx = max(mx, ae.w); }
+            if (mx > mn) { atomicMin(&S.smin, mn); atomicMax(&S.smax, mx); }
+        }
+    } else if (threadIdx.x == 0 && hi > lo) { S.smin = 0; S.smax = R.n; }
+    __syncthreads();
+    smin = S.smin; smax = S.smax;
+    if (!(smax > smin && (smax - smin) <= R2_STAGE)) { smin = 0; smax = 0; }
+}
+
 __device__ __forceinline__ double group_sum_rt(double v, int G) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -470,7 +525,8 @@ __device__ __forceinline__ double group_sum_rt(double v, int G) {
 // processed in rounds; each round gives every atom G lanes, G = the largest power of two that lets the round
 // cover at least half of what is left (64 atoms x 8 lanes, then 4 atoms x 32 lanes for 68 atoms on 512 threads).
 __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2* pos, double2* sdir, const int* oidx, int mode, double beta,
-                                              double scale, bool count_pairs, Relax2Smem& S, unsigned long long* tm = nullptr) {
+                                              double scale, bool count_pairs, Relax2Smem& S, unsigned int& parity, int smin, int smax,
+                                              bool issue_here, unsigned long long* tm = nullptr) {
 #define GMARK(k)                                                                          \
     if (tm && threadIdx.x == 0 && blockIdx.x == R.phase_block) {                          \
         const unsigned long long _t = gtimer();                                           \
@@ -485,6 +541,16 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
     ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = R.n;
     double mf = 0.0;
     unsigned long long visits = 0;
+    // The neighbourhood of this block's atoms [smin, smax) was determined after the last rebuild (relax2_stage_range);
+    // its positions are fetched by ONE TMA bulk copy (issued here, or earlier by the caller so that the copy overlaps
+    // the control arithmetic) and the sweep reads shared memory.
+    const bool staged = smax > smin && (smax - smin) <= R2_STAGE && R.debug != 6;
+    if (staged) {
+        if (issue_here && threadIdx.x == 0) bulk_load(S.stage, pos + smin, (unsigned int)(smax - smin) * 16u, &S.mbar);
+        mbar_wait(&S.mbar, parity);
+        parity ^= 1u;
+    }
+    const double2* npos = staged ? (S.stage - smin) : pos;       // neighbour positions by slot
     for (int r0 = lo; r0 < hi;) {
         const int rem = hi - r0;
         int G = 32;
@@ -501,9 +567,9 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
             const int4 ab = R.nbr[4 * slot], ae = R.nbr[4 * slot + 1], sb = R.nbr[4 * slot + 2], se = R.nbr[4 * slot + 3];
             if (ab.x >= 0) {        // stencil ranges cached at the last rebuild
                 if (P.aa_mode == 0) {
-                    for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
+                    for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, npos[s], P.E_a, P.ra2, ax, ay);
                 } else {
-                    flat_forces(P, pos, ab, ae, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
+                    flat_forces(P, npos, ab, ae, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
                 }
                 GMARK(12)
                 flat_forces(P, R.sub.sxy, sb, se, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
@@ -556,6 +622,10 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
 __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     __shared__ Relax2Smem S;
     unsigned int epoch = 0;
+    unsigned int tma_parity = 0;
+    int st_min = 0, st_max = 0;      // staged slot range of this block (relax2_stage_range)
+    if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
+    __syncthreads();
     const DevParams& P = R.P;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -696,6 +766,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(3)
         relax2_barrier(R, epoch);
         PHASE2_MARK(4)
+        // x_np is published: start the TMA copy of this block's neighbourhood now, it lands while beta is being formed
+        const bool early = st_max > st_min && R.debug != 6;
+        if (early && threadIdx.x == 0) bulk_load(S.stage, posn + st_min, (unsigned int)(st_max - st_min) * 16u, &S.mbar);
         // every block: beta and min-y from the same partials in the same order
         if (threadIdx.x < 32) {
             double t2 = 0.0, b2 = 0.0, m2 = INFINITY;
@@ -710,17 +783,21 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         const double beta = S.ctl[0] / S.ctl[1];                          // :143-145
         PHASE2_MARK(10)
         // ---------------- rebuild (rare) + G
+        bool issue_here = false;
         if (*R.need_rebuild) {
+            if (early) { mbar_wait(&S.mbar, tma_parity); tma_parity ^= 1u; }      // retire the copy of the stale order
+            issue_here = true;
             relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S);
             if (gtid == 0) *R.need_rebuild = 0;
             if (*R.n_items > R.item_cap) overflow = true;
             ++rebuilds;
+            relax2_stage_range(R, S, st_min, st_max);
             PHASE2_MARK(7)
             cs ^= 1;          // the rebuilt x_np now lives in pos[cur]: make it the "next" buffer by flipping cur
             cur ^= 1;
         }
         PHASE2_MARK(11)
-        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, &t_mark);
+        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, tma_parity, st_min, st_max, issue_here, &t_mark);
         PHASE2_MARK(5)
         relax2_barrier(R, epoch);
         PHASE2_MARK(6)
@@ -738,7 +815,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         if (scale > 1024) { scale = 16; threshold *= 10; }              // :111-113
         relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S);
         if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
-        relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S);   // dx0, sn = dx0  :120,125
+        relax2_stage_range(R, S, st_min, st_max);
+        relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true);   // dx0, sn = dx0  :120,125
         first_pass = false;
         relax2_barrier(R, epoch);
         line_search();                                                  // :121-129
