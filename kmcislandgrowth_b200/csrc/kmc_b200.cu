@@ -192,6 +192,7 @@ static DevParams to_dev(const KmcParams& p) {
     d.L = p.L; d.halfL = p.L / 2; d.bin_size = p.bin_size; d.Dmin = p.Dmin; d.Dmax = p.Dmax;
     d.E_a = p.E_a; d.r_a = p.r_a; d.E_as = p.E_as; d.r_as = p.r_as;
     d.ra2 = p.r_a * p.r_a; d.ras2 = p.r_as * p.r_as;
+    d.inv_ra2 = 1.0 / d.ra2; d.inv_ras2 = 1.0 / d.ras2;
     d.bond_a = 1.2 * p.r_a; d.bond_s = 1.2 * p.r_as;
     d.beta = p.beta; d.omega = p.omega; d.Rd = p.Rd;
     d.nbx = p.nbins_x; d.nby = p.nbins_y; d.ncell = p.nbins_x * p.nbins_y;

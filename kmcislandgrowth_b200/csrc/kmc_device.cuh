@@ -14,6 +14,7 @@ struct DevParams {
     double L, halfL, bin_size, Dmin, Dmax;
     double E_a, r_a, E_as, r_as;
     double ra2, ras2;        // r0^2 for the r^2-based LJ forms
+    double inv_ra2, inv_ras2;
     double bond_a, bond_s;   // 1.2*r_a, 1.2*r_as           (Bins.py:100,107)
     double beta, omega, Rd;
     int nbx, nby, ncell;     // ncell = nbx*nby ; cell id ncell = atoms outside the addressable grid
@@ -126,15 +127,14 @@ __device__ __forceinline__ int stencil_population(const DevParams& P, const Cell
     return m;
 }
 
-// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (x is a squared distance: finite, > 0 where used)
+// 1/x to ~1 ulp in three dependent FMAs: MUFU.RCP64H seed y0 (relative error e0 ~ 2^-23), then the cubically
+// convergent step y0*(1 + e0 + e0^2), truncation error e0^3 ~ 2^-69 (x is a squared distance: finite, > 0 where used)
 __device__ __forceinline__ double fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 }
 
 // ---- Lennard-Jones pair terms on r^2 (Energy.py:24,28 and :55-59) ------------------------------

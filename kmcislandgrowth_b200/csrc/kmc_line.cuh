@@ -66,13 +66,27 @@ __device__ __forceinline__ void pair_line_part(const DevParams& P, double dx0, d
         const double A = bx * bx + by * by;
         const double B = 2.0 * (bx * ddx + by * ddy);
         const double C = ddx * ddx + ddy * ddy;
+        // |d(a)| >= |d0| - (KC-1)|dd|: when that bound is positive no candidate can have r == 0 and the r > 0 test of
+        // Energy.py:28 is decided once per pair instead of once per candidate
+        if (A > (double)((KC - 1) * (KC - 1)) * C * 1.0000001 + 1e-30) {
+            // (r0/r)^2 = 1 / (r^2/r0^2): scaling the three coefficients once per pair saves a multiply per candidate
+            const double inv0 = (r0sq == P.ra2) ? P.inv_ra2 : P.inv_ras2;
+            const double As = A * inv0, Bs = B * inv0, Cs = C * inv0;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            const double r2 = fma((double)k, fma((double)k, C, B), A);
-            const double q2 = r0sq * fast_rcp(r2);
-            const double q6 = q2 * q2 * q2;
-            const double e = q6 * (q6 - 2.0);
-            acc[k] = (r2 > 0.0) ? fma(E, e, acc[k]) : acc[k];
+            for (int k = 0; k < NC; ++k) {
+                const double q2 = fast_rcp(fma((double)k, fma((double)k, Cs, Bs), As));
+                const double q6 = q2 * q2 * q2;
+                acc[k] = fma(E, q6 * (q6 - 2.0), acc[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const double r2 = fma((double)k, fma((double)k, C, B), A);
+                const double q2 = r0sq * fast_rcp(r2);
+                const double q6 = q2 * q2 * q2;
+                const double e = q6 * (q6 - 2.0);
+                acc[k] = (r2 > 0.0) ? fma(E, e, acc[k]) : acc[k];
+            }
         }
     } else {
 #pragma unroll
