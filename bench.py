@@ -57,7 +57,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", os.environ.get("KMC_BENCH_SMI_MS", "200")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag.is_set():
                     break
@@ -178,7 +178,7 @@ def workload_config(name, gv, ad):
             "substrate_atoms": int(gv.W * gv.Hs), "aa_mode": "bins3x3" if gv.aa_mode else "all_pairs",
             "event": "rates+select+hop/deposit+global relaxation (2DGrowth.py:317-329)",
             "replicas": "one trajectory per GPU, identical seeded uniform stream on every rank (fixed per-GPU work)",
-            "l2_note": "working set (<2 MB) fits L2 by construction of the workload; no L2 flush is possible inside the persistent kernel, inputs are rewritten every line search"}
+            "l2_flush": "256 MB buffer rewritten between events (inside the timed region); the working set (<2 MB) is L2 resident within an event by construction of the workload"}
 
 
 def load_fixture(name, first=0, count=None):
@@ -226,7 +226,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if not os.environ.get("KMC_BENCH_NO_SMI"):
+        sampler.start()
     # untimed set-up: bring the synthetic film to a relaxed state (bounded)
     st = ctx.relax(sim.sbins, 16, 1e-4, args.prerelax)
     nsteps = args.warmup + args.steps
@@ -242,6 +243,9 @@ def run_ours(args):
         return
     for s in range(args.warmup):
         sim.step(us[s, 0], us[s, 1], cap)
+    # L2 hygiene: the working set (< 2 MB) is far below the 126 MB L2, so a 256 MB buffer is rewritten between events
+    # (inside the timed regions, ~0.05 ms per step); within an event the persistent kernel necessarily runs from L2.
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
 
     # ---- timed region 1: device-resident trajectory
     state0 = sim.adatoms.copy()           # both timed regions run the SAME events from this state
@@ -255,6 +259,8 @@ def run_ours(args):
     e0.record()
     recs = []
     for s in range(args.steps):
+        if not args.no_flush:
+            flush.zero_()
         recs.append(sim.step(us[args.warmup + s, 0], us[args.warmup + s, 1], cap))
     e1.record()
     barrier()
@@ -276,6 +282,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     h2d = d2h = 0
     for s in range(args.steps):
+        if not args.no_flush:
+            flush.zero_()
         ctx.state_set(host.numpy())
         h2d += host.numel() * 8
         rec = sim.step(us[args.warmup + s, 0], us[args.warmup + s, 1], cap)
@@ -374,6 +382,7 @@ def main():
     ap.add_argument("--prerelax", type=int, default=4000)
     ap.add_argument("--ref-line-searches", type=int, default=6, help="line searches per bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="skip the 256 MB L2 flush between events")
     ap.add_argument("--record-fixture", action="store_true", help="record line searches per event of the seeded trajectory")
     args = ap.parse_args()
     if args.impl == "reference":

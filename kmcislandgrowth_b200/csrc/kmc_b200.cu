@@ -1205,15 +1205,15 @@ __global__ void k_remove_atom(const double2* __restrict__ in, int n, int k, doub
     if (i < n - 1) out[i] = in[i < k ? i : i + 1];
 }
 
-int kmc_hop_place(KmcCtx* c, const KmcBins* sb, int64_t k, double u) {
-    if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
+static int hop_place_impl(KmcCtx* c, const KmcBins* sb, int64_t k, double u, bool have_surface) {
     const int n = (int)c->st_n;
     if (k < 0 || k >= n) return fail(KMC_E_ARG, "hop index %lld out of range (n=%d)", (long long)k, n);
     uint8_t* surf;
     double* tmp;
     TRY(slot(c, S_OUT1, (size_t)n, &surf));
     TRY(slot(c, S_TMP0, 8, &tmp));
-    TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, nullptr, surf, nullptr, nullptr, nullptr, nullptr, nullptr));   // :239
+    // :239 SurfaceAtoms of the current state; kmc_event has just computed the same flags for the rate table
+    if (!have_surface) TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, nullptr, surf, nullptr, nullptr, nullptr, nullptr, nullptr));
     LAUNCH(c, "hop_target", k_hop_target, 1, 1024, c->dp, (const double2*)c->st_xy, surf, n, (int)k, u, tmp);          // :240-248
     CK(cudaGetLastError());
     TRY(mail(c, tmp, 3 * sizeof(double)));
@@ -1258,6 +1258,11 @@ int kmc_hop_place(KmcCtx* c, const KmcBins* sb, int64_t k, double u) {
     return 0;
 }
 
+int kmc_hop_place(KmcCtx* c, const KmcBins* sb, int64_t k, double u) {
+    if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
+    return hop_place_impl(c, sb, k, u, false);
+}
+
 int kmc_event(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_t max_ls, int32_t* kind_out, int64_t* hop_k_out, double* rtot_out,
               KmcRelaxStats* stats) {
     if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
@@ -1282,7 +1287,7 @@ int kmc_event(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_t max_ls
         const int64_t who = c->hp.hop_index_mode == 0 ? hres[0] : hres[1];       // :327
         if (kind_out) *kind_out = 1;
         if (hop_k_out) *hop_k_out = who;
-        TRY(kmc_hop_place(c, sb, who, u1));
+        TRY(hop_place_impl(c, sb, who, u1, true));      // S_OUT1 still holds the surface flags of this state
     } else {
         if (kind_out) *kind_out = 0;
         if (hop_k_out) *hop_k_out = -1;
