@@ -42,51 +42,58 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+class ClockSampler(object):
+    """SM clocks and throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py): the counters of
+    the recipe's nvidia-smi line.  Samples are taken by the MAIN thread between events of the timed loop (every few
+    steps): a concurrent poller -- nvidia-smi -lms or an NVML thread -- contends with the CUDA API calls of the event
+    loop for the driver lock and showed up as 5-8 ms outliers per event in 2 runs out of 5."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        threading.Thread.__init__(self, daemon=True)
-        self.index = index
         self.rows = []
-        self.stop_flag = threading.Event()
-        self.proc = None
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.h = None
+        self.how = "unavailable"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", os.environ.get("KMC_BENCH_SMI_MS", "200")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag.is_set():
-                    break
-                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.how = "nvml"
+        except Exception:
+            self.index = index
+
+    def sample(self):
+        if self.h is not None:
+            nv = self.nv
+            sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.rows.append((sm, self.mx, rs))
+            return
+        try:        # fallback: one nvidia-smi query
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout
+            c = [v.strip() for v in out.strip().split(",")]
+            rs = sum(bit for (name, bit), v in zip(self.REASONS, c[2:6]) if v.lower().startswith("active"))
+            self.rows.append((float(c[0]), float(c[1]), rs))
+            self.how = "nvidia-smi"
         except Exception:
             pass
 
-    def stop(self, t_begin=0.0, t_end=float("inf")):
-        """summary of the samples taken inside [t_begin, t_end] (the timed region)"""
-        self.stop_flag.set()
-        if self.proc is not None:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
-        sm, mx, reasons = [], [], set()
-        for (ts, r) in self.rows:
-            if ts < t_begin or ts > t_end:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+    def summary(self):
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": [name for name, bit in self.REASONS if bits & bit], "samples": len(self.rows), "via": self.how}
 
 
 def oracle_for(gv):
@@ -226,8 +233,6 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    if not os.environ.get("KMC_BENCH_NO_SMI"):
-        sampler.start()
     # untimed set-up: bring the synthetic film to a relaxed state (bounded)
     st = ctx.relax(sim.sbins, 16, 1e-4, args.prerelax)
     nsteps = args.warmup + args.steps
@@ -241,11 +246,13 @@ def run_ours(args):
         print(json.dumps(out))
         sim.close()
         return
-    for s in range(args.warmup):
-        sim.step(us[s, 0], us[s, 1], cap)
     # L2 hygiene: the working set (< 2 MB) is far below the 126 MB L2, so a 256 MB buffer is rewritten between events
     # (inside the timed regions, ~0.05 ms per step); within an event the persistent kernel necessarily runs from L2.
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    for s in range(args.warmup):          # warm-up events, with the flush (its first call costs tens of ms: lazy module load)
+        flush.zero_()
+        sim.step(us[s, 0], us[s, 1], cap)
+    sampler.sample()
 
     # ---- timed region 1: device-resident trajectory
     state0 = sim.adatoms.copy()           # both timed regions run the SAME events from this state
@@ -258,10 +265,15 @@ def run_ours(args):
     t_begin1 = t0
     e0.record()
     recs = []
+    step_wall = []
     for s in range(args.steps):
         if not args.no_flush:
             flush.zero_()
+        _ts = time.perf_counter()
         recs.append(sim.step(us[args.warmup + s, 0], us[args.warmup + s, 1], cap))
+        step_wall.append(time.perf_counter() - _ts)
+        if s % max(1, args.steps // 5) == 0 or s == args.steps - 1:
+            sampler.sample()          # inside the timed region, between two events
     e1.record()
     barrier()
     t_end = time.perf_counter()
@@ -295,7 +307,7 @@ def run_ours(args):
             host = torch.from_numpy(out.copy()).pin_memory()
     barrier()
     t_e2e = time.perf_counter() - t0
-    clocks = sampler.stop(t_begin1, t_end)
+    clocks = sampler.summary()
 
     tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -334,6 +346,7 @@ def run_ours(args):
             "us_per_line_search": t_dev / max(sum(ls), 1) * 1e6,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": int(launches), "wall_s_timed_region": wall_dev,
+            "step_wall_ms": [round(1e3 * v, 2) for v in step_wall],
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_relax2 (persistent: one launch = one Relaxation; per line search 20 candidate energies + 1 force sweep)",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
