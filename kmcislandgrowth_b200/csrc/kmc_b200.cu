@@ -1020,6 +1020,7 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
     else if (n <= 256 && !getenv("KMC_NO_CLUSTER")) { blocks = std::min(blocks, 8); sync_mode = 2; }
     const int G = 0;
     if (c->item_cap == 0) c->item_cap = (size_t)n * 4 + (size_t)c->dp.ncell * 2 + 1024;
+    if (const char* e = getenv("KMC_ITEM_CAP")) c->item_cap = (size_t)std::max(1, atoi(e));      // tests: force the grow-and-relaunch path
     for (int attempt = 0; attempt < 8; ++attempt) {
         Relax2Args R{};
         R.P = c->dp; R.sub = view_of(sb); R.n = n; R.ncell2 = c->dp.ncell + 2;

@@ -388,6 +388,35 @@ def test_checkpoint_and_island_statistics(tmp_path):
     sim2.close()
 
 
+def test_work_list_overflow_relaunch_and_large_deposit(monkeypatch):
+    """(1) a work list that is too small makes the persistent kernel stop and the host grow it and relaunch from the
+    untouched state: same result as with a large list; (2) DepositAdatom on the 10k-adatom film (top-down probe)."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv, sub, ad = workloads.make("cfg2_256x256_10k")
+    out = {}
+    for cap in (None, "64"):
+        if cap:
+            monkeypatch.setenv("KMC_ITEM_CAP", cap)
+        ctx = runtime.Context(runtime.params_from(gv), 0)
+        sb = ctx.bins_create(sub)
+        ctx.state_set(ad)
+        st = ctx.relax(sb, 16, 1e-4, 25)
+        out[cap] = (ctx.state_get(), int(st.line_searches))
+        if cap is None:
+            n0 = ctx.state_count()
+            ctx.deposit_place(sb, 0.3)
+            assert ctx.state_count() == n0 + 1
+            new = ctx.state_get()[-2:]
+            o = _oracle_for(gv)
+            want = o.DepositPlace(out[None][0], o.PutInBins(sub), 0.3)[-2:]
+            assert np.array_equal(new, want)
+        sb.close()
+        ctx.close()
+        monkeypatch.delenv("KMC_ITEM_CAP", raising=False)
+    assert out["64"][1] == out[None][1] == 25
+    assert np.array_equal(out["64"][0], out[None][0])
+
+
 def test_block_scan_selection_matches_sequential_order():
     """kmc_select's block-scan path (large tables) against the reference-order selection: identical index for
     random u; a mismatch is only legal when r sits within rounding of a partial sum (none expected here)."""
