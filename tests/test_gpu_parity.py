@@ -417,6 +417,34 @@ def test_work_list_overflow_relaunch_and_large_deposit(monkeypatch):
     assert np.array_equal(out["64"][0], out[None][0])
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16, 17, 18])
+def test_seeded_trajectories_match_the_oracle(seed):
+    """KMC trajectories over several seeds (default constants, reference quirk modes, relaxation capped at 1500 line
+    searches on both sides): event kinds, hop indices, total rates, adatom counts, positions and the island statistics
+    (north_star: island density / size distributions over seeds) agree event by event."""
+    from kmcislandgrowth_b200 import Growth, workloads
+    o = orc.Oracle()
+    osb = o.PutInBins(orc.init_substrate(18, 10, 2.7, 48.6))
+    gv = workloads.constants_for(18)
+    rng = np.random.default_rng(seed)
+    us = rng.uniform(0, 1, (16, 2))
+    sim = Growth.Simulation()
+    ad = np.zeros(0)
+    try:
+        for t in range(16):
+            ad, kind, hk, rtot, st, rc = o.Event(ad, osb, us[t], max_line_searches=1500)
+            rec = sim.step(us[t, 0], us[t, 1], max_line_searches=1500)
+            assert (rec["kind"], rec["hop_k"]) == (kind, hk), (seed, t)
+            assert abs(rec["rtot"] - rtot) <= 1e-8 * abs(rtot)
+            assert rec["line_searches"] == st.line_searches, (seed, t, rec["line_searches"], st.line_searches)
+            got = sim.adatoms
+            assert got.size == ad.size and np.max(np.abs(got - ad)) < 1e-5, (seed, t)
+            assert Growth.IslandStatistics(got, gv) == Growth.IslandStatistics(ad, gv)
+            sim.set_adatoms(ad)          # continue both from the oracle's state: one ulp cannot cascade
+    finally:
+        sim.close()
+
+
 def test_block_scan_selection_matches_sequential_order():
     """kmc_select's block-scan path (large tables) against the reference-order selection: identical index for
     random u; a mismatch is only legal when r sits within rounding of a partial sum (none expected here)."""
