@@ -1046,9 +1046,10 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         TRY(slot(c, S_FIX, (size_t)n * KC, &R.fix));
         TRY(slot(c, S_RED, (size_t)blocks * 4, &R.red));
         unsigned char* sync;
-        TRY(slot(c, S_SYNC, 256, &sync));
-        CK(cudaMemsetAsync(sync, 0, 256, c->stream));
+        TRY(slot(c, S_SYNC, 512, &sync));
+        CK(cudaMemsetAsync(sync, 0, 512, c->stream));
         R.barrier = (unsigned int*)sync;
+        R.hist = (unsigned long long*)(sync + 256);
         R.need_rebuild = (int*)(sync + 16);
         R.n_items = (int*)(sync + 20);
         R.n_movers = (int*)(sync + 24);
@@ -1060,8 +1061,14 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         R.debug = getenv("KMC_DEBUG_E") ? atoi(getenv("KMC_DEBUG_E")) : 0;
         R.phase_block = !getenv("KMC_PHASE_TIMING") ? -1 : (getenv("KMC_PHASE_BLOCK") ? std::min(atoi(getenv("KMC_PHASE_BLOCK")), blocks - 1) : 0);
         TRY(launch_relax2(c, R, blocks));
-        TRY(mail(c, sync, 256));
+        TRY(mail(c, sync, 512));
         const char* hm = (const char*)c->h_mail;
+        if (R.debug == 7) {     // diagnostics: per-atom displacement over a whole line (19/20/scale*|s|), decades from 1e-6 A
+            const unsigned long long* h = (const unsigned long long*)(hm + 256);
+            fprintf(stderr, "[kmc2 disp hist]");
+            for (int k = 0; k < 16; ++k) fprintf(stderr, " %llu", h[k]);
+            fprintf(stderr, "\n");
+        }
         const KmcRelaxStatsDev* ds = (const KmcRelaxStatsDev*)(hm + 64);
         if (ds->status == -4) {            // work list overflow: grow and run again (x0 is untouched)
             const int need = *(const int*)(hm + 20);

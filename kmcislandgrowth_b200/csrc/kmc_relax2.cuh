@@ -67,6 +67,7 @@ struct Relax2Args {
     long long max_ls;
     KmcRelaxStatsDev* stats;
     unsigned long long* phase_ns;
+    unsigned long long* hist;   // diagnostics (debug == 7): histogram of per-atom line displacements
     int phase_block;        // which block's thread 0 keeps the phase timers (diagnostics)
     int sync_mode;          // 0: global atomic barrier (cooperative launch), 1: one block (__syncthreads), 2: one thread-block cluster (hardware barrier)
     int debug;              // diagnostics only: 1 = energy phase skips the pair arithmetic, 2 = skips the work items
@@ -598,6 +599,12 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
             }
             sdir[slot] = sn;
             R.flag[slot] = (R.debug == 4) ? 0 : mover_flag(P, pi, sn, scale);
+            if (R.debug == 7) {
+                const double d = sqrt(sn.x * sn.x + sn.y * sn.y) * (double)(KC - 1) / (20.0 * scale);
+                int b = (int)floor(2.0 * (log10(fmax(d, 1e-30)) + 6.0));       // half decades from 1e-6
+                b = max(0, min(15, b));
+                atomicAdd(&R.hist[b], 1ull);
+            }
         }
         GMARK(15)
         r0 += groups;

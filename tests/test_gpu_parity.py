@@ -445,6 +445,40 @@ def test_seeded_trajectories_match_the_oracle(seed):
         sim.close()
 
 
+@pytest.mark.parametrize("aa", [0, 1])
+def test_relaxation_with_y_wrapped_stencils(aa):
+    """A pillar that reaches the top bin row: there the stencil's y indices wrap ONCE to row 0 (Bins.py:62-65), i.e.
+    the top of the pillar 'sees' the bottom substrate rows, and atoms above the grid are invisible to others.  All
+    engines must follow the oracle through these non-contiguous stencils (generic stencil walk, three-range items)."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(18, 10, 10, aa_mode=aa)
+    sub = workloads.substrate(gv)
+    pts = []
+    for layer in range(1, 15):            # up to y = 32.7 A: rows 3 .. 6 of 7, the last layers above the top row
+        y = layer * gv.r_a * gv.sqrt3 / 2
+        for k in range(3):
+            pts.append((k * gv.r_a + (gv.r_a / 2 if layer % 2 == 1 else 0.0) - 2.7, y))
+    rng = np.random.default_rng(4)
+    ad = (np.asarray(pts) + rng.normal(0, 0.03, (len(pts), 2))).reshape(-1)
+    o = _oracle_for(gv)
+    osb = o.PutInBins(sub)
+    assert max(o.BinIndex(ad[2 * i], ad[2 * i + 1])[1] for i in range(len(pts))) >= gv.nbins_y - 1
+    xo, sto, rc = o.Relaxation(ad, osb, max_line_searches=60)
+    Fo = o.AdatomAdatomForces(ad) + o.AdatomSubstrateForces(ad, osb)
+    for mode in (0, 1, 2):
+        ctx = runtime.Context(runtime.params_from(gv), 0)
+        ctx.set_relax_mode(mode)
+        sb = ctx.bins_create(sub)
+        assert np.max(np.abs(ctx.forces(ad, sb, 3) - Fo)) < 1e-9 * max(1.0, np.max(np.abs(Fo)))
+        assert abs(ctx.relax_energy(ad, sb)[0] - o.RelaxEnergy((ad, osb))) < 1e-10 * abs(o.RelaxEnergy((ad, osb)))
+        ctx.state_set(ad)
+        st = ctx.relax(sb, 16, 1e-4, 60)
+        assert (int(st.line_searches), int(st.restarts)) == (int(sto.line_searches), int(sto.restarts)), mode
+        assert np.max(np.abs(ctx.state_get() - xo)) < 1e-7, mode
+        sb.close()
+        ctx.close()
+
+
 def test_block_scan_selection_matches_sequential_order():
     """kmc_select's block-scan path (large tables) against the reference-order selection: identical index for
     random u; a mismatch is only legal when r sits within rounding of a partial sum (none expected here)."""
