@@ -1042,7 +1042,7 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         TRY(slot(c, S_ITEMS, c->item_cap, &R.items));
         R.item_cap = (int)c->item_cap;
         TRY(slot(c, S_MOVERS, (size_t)n, &R.movers));
-        TRY(slot(c, S_LPART, (size_t)std::max(blocks, LINE_BLOCKS) * KC, &R.partial));
+        TRY(slot(c, S_LPART, (size_t)std::max(blocks, LINE_BLOCKS) * R2_NE, &R.partial));
         TRY(slot(c, S_FIX, (size_t)n * KC, &R.fix));
         TRY(slot(c, S_RED, (size_t)blocks * 4, &R.red));
         unsigned char* sync;

@@ -98,6 +98,80 @@ __device__ __forceinline__ void pair_line_part(const DevParams& P, double dx0, d
     }
 }
 
+// ---- Taylor form of the line energy ------------------------------------------------------------------
+// Along a line the squared distance of a pair is r^2(t) = A (1 + u(t)), u = b t + c t^2, with t = a - 9.5 measured
+// from the MIDDLE candidate, so its energy E (q^6 (1+u)^-6 - 2 q^3 (1+u)^-3), q = r0^2/A, is a power series in u
+// whose term u^k is O(w^k), w = relative change of r along half the line.  In the relaxation's steady state w is
+// 1e-6..1e-3 for all but a handful of pairs, so the degree-PD polynomial in t is exact to rounding (the first
+// dropped term is 792 u^7 < 2e-15 for |u| < POLY_UMAX) and the pair costs ~90 FP64 instructions instead of
+// 13 per candidate x 20; the PD+1 coefficients are summed over pairs and the 20 candidates are evaluated ONCE.
+// Side effect: the candidate DIFFERENCES are carried by the small coefficients 1..PD, i.e. they no longer
+// drown in the rounding of the ~6e4 eV total.  Pairs that move more (|u| >= POLY_UMAX), that can cross the +-L/2
+// seam along the line, or that can reach r = 0 are not expanded: the caller evaluates them per candidate
+// (pair_line_one), exactly as before.
+constexpr int PD = 6;
+constexpr double POLY_UMAX = 3e-3;
+
+// returns false when the pair must take the per-candidate path; inv0 = 1/r0^2
+__device__ __forceinline__ bool pair_line_poly(const DevParams& P, double dx0, double dy0, double ddx, double ddy, double E,
+                                               double inv0, double (&acc)[PD + 1]) {
+    constexpr double tm = 0.5 * (KC - 1);
+    const double mx = fma(tm, ddx, dx0), my = fma(tm, ddy, dy0);      // displacement at the middle of the line
+    const double A = fma(mx, mx, my * my);
+    const double Bh = fma(mx, ddx, my * ddy);                         // B/2
+    const double C = fma(ddx, ddx, ddy * ddy);
+    const bool no_wrap = fabs(dx0) + (KC - 1) * fabs(ddx) < P.halfL - 1e-9;
+    const bool quiet = fma(C, tm * tm, 2.0 * tm * fabs(Bh)) < POLY_UMAX * A;      // strict: A == 0 is never quiet
+    if (!(no_wrap && quiet)) return false;
+    const double q = fast_rcp(A * inv0);          // r0^2 / A
+    const double w = q * inv0;                    // 1 / A
+    const double b = (Bh + Bh) * w, c = C * w;
+    const double q3 = q * q * q;
+    const double Q3 = E * q3, Q6 = Q3 * q3;
+    // e(u) = sum_k g_k u^k,  g_k = (-1)^k (C(k+5,5) Q6 - 2 C(k+2,2) Q3)
+    const double g0 = fma(1.0, Q6, -2.0 * Q3);
+    const double g1 = fma(-6.0, Q6, 6.0 * Q3);
+    const double g2 = fma(21.0, Q6, -12.0 * Q3);
+    const double g3 = fma(-56.0, Q6, 20.0 * Q3);
+    const double g4 = fma(126.0, Q6, -30.0 * Q3);
+    const double g5 = fma(-252.0, Q6, 42.0 * Q3);
+    const double g6 = fma(462.0, Q6, -56.0 * Q3);
+    // composition G(u(t)) by Horner in u, every intermediate truncated to the degree that can still reach t^PD:
+    // P_k = g_k + u P_{k+1}, deg P_k = PD - k;  (u p)[m] = b p[m-1] + c p[m-2]
+    double p0 = g6, p1, p2, p3, p4, p5;
+    p1 = b * p0;                                                  p0 = g5;       // P5: degree 1
+    p2 = fma(b, p1, c * p0); p1 = b * p0;                         p0 = g4;       // P4: degree 2
+    p3 = fma(b, p2, c * p1); p2 = fma(b, p1, c * p0); p1 = b * p0; p0 = g3;      // P3
+    p4 = fma(b, p3, c * p2); p3 = fma(b, p2, c * p1); p2 = fma(b, p1, c * p0); p1 = b * p0; p0 = g2;   // P2
+    p5 = fma(b, p4, c * p3); p4 = fma(b, p3, c * p2); p3 = fma(b, p2, c * p1); p2 = fma(b, p1, c * p0); p1 = b * p0; p0 = g1;   // P1
+    // P0 = g0 + u P1, accumulated directly
+    acc[6] = fma(b, p5, fma(c, p4, acc[6]));
+    acc[5] = fma(b, p4, fma(c, p3, acc[5]));
+    acc[4] = fma(b, p3, fma(c, p2, acc[4]));
+    acc[3] = fma(b, p2, fma(c, p1, acc[3]));
+    acc[2] = fma(b, p1, fma(c, p0, acc[2]));
+    acc[1] = fma(b, p0, acc[1]);
+    acc[0] += g0;
+    return true;
+}
+
+// one candidate of one pair, general form (min-image wrap per candidate, r == 0 excluded: Periodic.py:8-20, Energy.py:28)
+__device__ __forceinline__ double pair_line_one(const DevParams& P, double dx0, double dy0, double ddx, double ddy, double E,
+                                                double r0sq, int a) {
+    const double dx = put_in_box(fma((double)a, ddx, dx0), P.L, P.halfL);
+    const double dy = fma((double)a, ddy, dy0);
+    return lj_energy(dx * dx + dy * dy, E, r0sq);
+}
+
+// value of the summed polynomial at candidate a
+__device__ __forceinline__ double poly_at(const double* cf, int a) {
+    const double t = (double)a - 0.5 * (KC - 1);
+    double v = cf[PD];
+#pragma unroll
+    for (int m = PD - 1; m >= 0; --m) v = fma(v, t, cf[m]);
+    return v;
+}
+
 struct LineArgs {
     DevParams P;
     CellView ad;                 // base cell list of x (ad.sxy[slot] == x[ad.sidx[slot]])

@@ -19,9 +19,9 @@
 namespace kmc {
 
 constexpr int R2_THREADS = 512;
-constexpr int R2_LP = 1;            // lanes per pair in the energy phase
-constexpr int R2_NC = KC / R2_LP;   // candidates per lane
+constexpr int R2_NE = KC + PD + 1;  // values reduced per line search: KC per-candidate sums (pairs that are not expanded) + the polynomial
 constexpr int R2_CHUNK = 64;        // pairs per work item
+constexpr int R2_WI = 8;           // work items of a warp cached in shared memory between rebuilds
 constexpr int R2_PARTS = 8;         // per home cell: adatom columns 0..3, substrate columns 0..3
 
 struct WorkItem {
@@ -56,7 +56,8 @@ struct Relax2Args {
     int item_cap;
     int* movers;            // slots of the movers, ascending
     int* n_movers;
-    double* partial;        // [KC][gridDim] candidate partial sums (transposed: coalesced reads)
+    double* partial;        // [R2_NE][gridDim] partial sums (transposed: coalesced reads): KC candidate sums of the pairs evaluated
+                            // per candidate, then the PD+1 polynomial coefficients of all other pairs (pair_line_poly)
     double* fix;            // [n][KC]
     double* red;            // [gridDim][4] top, bot, miny, maxF
     unsigned int* barrier;
@@ -95,8 +96,10 @@ struct Relax2Smem {
     alignas(8) unsigned long long mbar;      // mbarrier the bulk copy completes on
     int smin, smax;
     int scan[R2_THREADS];
-    double wred[R2_THREADS / 32][KC];
-    double e[KC];
+    double wred[R2_THREADS / 32][R2_NE];
+    WorkItem wit[R2_THREADS / 32][R2_WI];    // this block's warps' first work items (static dealing: valid until the next rebuild)
+    double e[R2_NE];
+    int amin;
     double ctl[4];
     double red[32];
 };
@@ -332,35 +335,97 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
     relax2_barrier(R, epoch);
 }
 
-// ---- E: one work item ----------------------------------------------------------------------------
-__device__ __forceinline__ void relax2_item(const Relax2Args& R, const WorkItem& it, const double2* pos, const double2* sdir,
-                                            double inv_step, int lane, double (&acc)[R2_NC]) {
-    const DevParams& P = R.P;
-    const bool is_sub = (it.kind & 8) != 0;
-    const int a0 = (lane & (R2_LP - 1)) * R2_NC;
-    for (int q = it.begin + lane / R2_LP; q < it.begin + it.count; q += 32 / R2_LP) {
-        int j = (int)((float)q * it.inv_nh);                    // q / nh with one fix-up step (pair spaces stay far below 2^23)
-        int i = q - j * it.nh;
-        if (i < 0) { --j; i += it.nh; } else if (i >= it.nh) { ++j; i -= it.nh; }
-        const int hs = it.hb + i;
-        int js, self;
-        if (j < it.n0) { js = it.b0 + j; self = it.kind & 1; }
-        else if (j < it.n0 + it.n1) { js = it.b1 + (j - it.n0); self = it.kind & 2; }
-        else { js = it.b2 + (j - it.n0 - it.n1); self = it.kind & 4; }
-        if (R.flag[hs]) continue;                               // movers are handled by the fix-up phase
-        const double2 pi = pos[hs], si = sdir[hs];
-        if (is_sub) {
-            const double2 pj = R.sub.sxy[js];
-            const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
-            pair_line_part<R2_NC>(P, dx0, pj.y - pi.y, -si.x * inv_step, -si.y * inv_step, P.E_as, P.ras2, a0, acc);
-        } else {
-            if (R.flag[js] || (self && js <= hs)) continue;
-            const double2 pj = pos[js], sj = sdir[js];
-            const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
-            if (R.debug == 1) { acc[0] += dx0 + sj.x + sj.y + pj.y; continue; }
-            pair_line_part<R2_NC>(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, a0, acc);
+// ---- E: work items --------------------------------------------------------------------------------
+// One pair per lane and round.  Quiet pairs add their Taylor coefficients to acc (pair_line_poly).  Pairs that cannot be
+// expanded are evaluated per candidate by the WARP: each one is broadcast and lane a (< KC) adds candidate a to its private
+// sum `eslow` (fixed order: deterministic; one register instead of KC accumulators per lane).
+__device__ __forceinline__ void relax2_pair_round(const DevParams& P, bool valid, double dx0, double dy0, double ddx, double ddy, bool is_sub,
+                                                  int lane, double (&acc)[PD + 1], double& eslow) {
+    const double E = is_sub ? P.E_as : P.E_a;
+    bool slow = false;
+    if (valid) slow = !pair_line_poly(P, dx0, dy0, ddx, ddy, E, is_sub ? P.inv_ras2 : P.inv_ra2, acc);
+    unsigned int m = __ballot_sync(0xffffffffu, slow);
+    if (m) {
+        const double r0sq = is_sub ? P.ras2 : P.ra2;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const double bx = __shfl_sync(0xffffffffu, dx0, src), by = __shfl_sync(0xffffffffu, dy0, src);
+            const double vx = __shfl_sync(0xffffffffu, ddx, src), vy = __shfl_sync(0xffffffffu, ddy, src);
+            if (lane < KC) eslow += pair_line_one(P, bx, by, vx, vy, E, r0sq, lane);
         }
     }
+}
+
+// operands of one round of a work item: every load is issued before any of them is used (one L2 round trip), and the
+// caller keeps two rounds in flight (after a grid barrier every access is an L2 hit of ~0.45 us; items come from shared memory)
+struct PairLoad {
+    double2 pi, si, pj, sj;
+    int hs, js;
+    unsigned int bits;      // 0: in range, 1: same-cell rule applies, 2: substrate partner, 8..: flag[hs], 16..: flag[js]
+};
+__device__ __forceinline__ PairLoad relax2_round_load(const Relax2Args& R, const WorkItem& it, int q0, const double2* pos, const double2* sdir, int lane) {
+    PairLoad L;
+    const bool is_sub = (it.kind & 8) != 0;
+    const int end = it.begin + it.count;
+    const int q = min(q0 + lane, end - 1);
+    int j = (int)((float)q * it.inv_nh);                    // q / nh with one fix-up step (pair spaces stay far below 2^23)
+    int i = q - j * it.nh;
+    if (i < 0) { --j; i += it.nh; } else if (i >= it.nh) { ++j; i -= it.nh; }
+    const int hs = it.hb + i;
+    int js, self;
+    if (j < it.n0) { js = it.b0 + j; self = it.kind & 1; }
+    else if (j < it.n0 + it.n1) { js = it.b1 + (j - it.n0); self = it.kind & 2; }
+    else { js = it.b2 + (j - it.n0 - it.n1); self = it.kind & 4; }
+    L.hs = hs; L.js = js;
+    const unsigned int fh = R.flag[hs];
+    const unsigned int fj = is_sub ? 0u : (unsigned int)R.flag[js];
+    L.pi = pos[hs];
+    L.si = sdir[hs];
+    L.pj = is_sub ? R.sub.sxy[js] : pos[js];
+    L.sj = is_sub ? make_double2(0.0, 0.0) : sdir[js];
+    L.bits = ((q0 + lane < end) ? 1u : 0u) | (self ? 2u : 0u) | (is_sub ? 4u : 0u) | (fh << 8) | (fj << 16);
+    return L;
+}
+__device__ __forceinline__ void relax2_round_compute(const Relax2Args& R, const PairLoad& L, double inv_step, int lane, double (&acc)[PD + 1], double& eslow) {
+    const DevParams& P = R.P;
+    const bool is_sub = (L.bits & 4u) != 0;       // warp uniform (a property of the item)
+    // movers are handled by the fix-up phase; pairs inside the home cell count once (slot_i < slot_j)
+    const bool valid = (L.bits & 1u) && !(L.bits >> 8) && !((L.bits & 2u) && L.js <= L.hs);
+    const double dx0 = put_in_box(L.pj.x - L.pi.x, P.L, P.halfL);
+    const double dy0 = L.pj.y - L.pi.y;
+    const double ddx = (L.sj.x - L.si.x) * inv_step, ddy = (L.sj.y - L.si.y) * inv_step;
+    if (R.debug == 1) { if (valid) acc[0] += dx0 + dy0 + ddx + ddy; return; }
+    relax2_pair_round(P, valid, dx0, dy0, ddx, ddy, is_sub, lane, acc, eslow);
+}
+
+
+// all items k = w0, w0 + nw, ... of this warp; `wit` = the warp's cached copies of the first R2_WI of them
+__device__ __forceinline__ void relax2_items(const Relax2Args& R, const WorkItem* wit, int w0, int nw, int n_items, const double2* pos,
+                                             const double2* sdir, double inv_step, int lane, double (&acc)[PD + 1], double& eslow) {
+    if (w0 < 0 || w0 >= n_items) return;
+    int idx = 0;                            // ordinal of the current item of this warp
+    WorkItem it = wit[0];
+    int q0 = it.begin;
+    PairLoad cur = relax2_round_load(R, it, q0, pos, sdir, lane);
+    for (;;) {
+        // advance to the next round
+        bool more = true;
+        q0 += 32;
+        if (q0 >= it.begin + it.count) {
+            ++idx;
+            const int k = w0 + idx * nw;
+            if (k < n_items) {
+                it = (idx < R2_WI) ? wit[idx] : R.items[k];
+                q0 = it.begin;
+            } else more = false;
+        }
+        if (!more) break;
+        const PairLoad nxt = relax2_round_load(R, it, q0, pos, sdir, lane);
+        relax2_round_compute(R, cur, inv_step, lane, acc, eslow);
+        cur = nxt;
+    }
+    relax2_round_compute(R, cur, inv_step, lane, acc, eslow);
 }
 
 // ---- F: one (mover, candidate) by one warp; sorted-state version of line_fix_one ------------------
@@ -495,6 +560,17 @@ __device__ __forceinline__ void flat_forces(const DevParams& P, const double2* p
 // adjacent columns) except at the periodic seam.  Valid until the next rebuild.
 __device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Smem& S, int& smin, int& smax) {
     const int T = blockDim.x;
+    {   // cache this warp's first work items (the dealing of the energy phase: item k -> warp k mod nw, block 0 excluded)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+        const int wpb = blockDim.x >> 5;
+        const int w0 = gridDim.x > 1 ? gwarp - wpb : gwarp, nw = gridDim.x > 1 ? nwarps - wpb : nwarps;
+        const int n_items = min(*R.n_items, R.item_cap);
+        if (w0 >= 0 && lane < R2_WI) {
+            const int k = w0 + lane * nw;
+            if (k < n_items) S.wit[warp][lane] = R.items[k];
+        }
+    }
     const int per = (R.n + gridDim.x - 1) / gridDim.x;
     const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
     __syncthreads();
@@ -679,39 +755,42 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 if (R.flag[i]) R.movers[p++] = i;
             if (t == T - 1) *R.n_movers = S.scan[t];
         }
-        double acc[R2_NC];
+        double acc[PD + 1];
 #pragma unroll
-        for (int a = 0; a < R2_NC; ++a) acc[a] = 0.0;
+        for (int a = 0; a <= PD; ++a) acc[a] = 0.0;
+        double eslow = 0.0;                     // lane a < KC: candidate a of the pairs evaluated per candidate
         const int n_items = *R.n_items;
         {   // block 0 builds the mover list; when other blocks exist they share the items among themselves
             const int wpb = R2_THREADS / 32;
             const int w0 = nblk > 1 ? gwarp - wpb : gwarp, nw = nblk > 1 ? nwarps - wpb : nwarps;
-            if (w0 >= 0 && R.debug != 2)
-                for (int k = w0; k < n_items; k += nw) {
-                    const WorkItem it = R.items[k];
-                    relax2_item(R, it, pos, sdir, inv_step, lane, acc);
-                }
+            if (R.debug != 2) relax2_items(R, S.wit[warp], w0, nw, n_items, pos, sdir, inv_step, lane, acc, eslow);
         }
         if (P.aa_mode == 0) {
-            const int a0 = (lane & (R2_LP - 1)) * R2_NC;
             for (int i = gwarp; i < R.n; i += nwarps) {
                 const double2 pi = pos[i], si = sdir[i];
-                for (int j = i + 1 + lane / R2_LP; j < R.n; j += 32 / R2_LP) {
-                    const double2 pj = pos[j], sj = sdir[j];
-                    const double dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
-                    pair_line_part<R2_NC>(P, dx0, pj.y - pi.y, (sj.x - si.x) * inv_step, (sj.y - si.y) * inv_step, P.E_a, P.ra2, a0, acc);
+                for (int j0 = i + 1; j0 < R.n; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool valid = j < R.n;
+                    double dx0 = 0.0, dy0 = 0.0, ddx = 0.0, ddy = 0.0;
+                    if (valid) {
+                        const double2 pj = pos[j], sj = sdir[j];
+                        dx0 = put_in_box(pj.x - pi.x, P.L, P.halfL);
+                        dy0 = pj.y - pi.y;
+                        ddx = (sj.x - si.x) * inv_step; ddy = (sj.y - si.y) * inv_step;
+                    }
+                    relax2_pair_round(P, valid, dx0, dy0, ddx, ddy, false, lane, acc, eslow);
                 }
             }
         }
+        double* wrow = S.wred[warp];            // this warp's row: [0,KC) per-candidate sums, [KC, R2_NE) polynomial
+        if (lane < KC) wrow[lane] = eslow;
 #pragma unroll
-        for (int a = 0; a < R2_NC; ++a) {      // sum over the lanes holding the same candidates (same lane parity)
-            double v = acc[a];
-#pragma unroll
-            for (int o = 16; o >= R2_LP; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane < R2_LP) S.wred[warp][lane * R2_NC + a] = v;
+        for (int a = 0; a <= PD; ++a) {
+            const double v = group_sum<32>(acc[a]);
+            if (lane == 0) wrow[KC + a] = v;
         }
         __syncthreads();
-        if (threadIdx.x < KC) {
+        if (threadIdx.x < R2_NE) {
             double v = 0.0;
             for (int w = 0; w < R2_THREADS / 32; ++w) v += S.wred[w][threadIdx.x];
             R.partial[(size_t)threadIdx.x * nblk + blockIdx.x] = v;
@@ -733,20 +812,29 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         // ---------------- S
         double2 pre_p = make_double2(0, 0), pre_s = make_double2(0, 0);      // issued ahead of the candidate sums
         if (gtid < R.n) { pre_p = pos[gtid]; pre_s = sdir[gtid]; }
-        for (int a = warp; a < KC; a += R2_THREADS / 32) {
+        for (int a = warp; a < R2_NE; a += R2_THREADS / 32) {
             double v = 0.0;
             for (int b = lane; b < nblk; b += 32) v += R.partial[(size_t)a * nblk + b];
-            for (int r = lane; r < nm; r += 32) v += R.fix[(size_t)r * KC + a];
+            if (a < KC)
+                for (int r = lane; r < nm; r += 32) v += R.fix[(size_t)r * KC + a];
             v = group_sum<32>(v);
             if (lane == 0) S.e[a] = v;
         }
         __syncthreads();
-        int amin = 0;
-        {
-            double em = S.e[0];
-            for (int a = 1; a < KC; ++a)
-                if (S.e[a] < em) { em = S.e[a]; amin = a; }                // first argmin, 2DGrowth.py:123,155
+        if (warp == 0) {        // candidate energies = polynomial + per-candidate sums; first argmin (2DGrowth.py:123,155)
+            double ev = INFINITY;
+            int ai = lane;
+            if (lane < KC) ev = poly_at(S.e + KC, lane) + S.e[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, ev, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, ai, o);
+                if (ov < ev || (ov == ev && oi < ai)) { ev = ov; ai = oi; }
+            }
+            if (lane == 0) S.amin = ai;
         }
+        __syncthreads();
+        const int amin = S.amin;
         double top = 0.0, bot = 0.0, my = INFINITY;
         for (int slot = gtid; slot < R.n; slot += gthreads) {
             const double2 p0 = (slot == gtid) ? pre_p : pos[slot];
