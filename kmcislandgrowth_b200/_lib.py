@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkmcb200.so")
+LIB_PATH = os.environ.get("KMC_LIB_PATH") or os.path.join(HERE, "libkmcb200.so")      # override: development builds only
 
 KMC_HOST, KMC_DEVICE = 0, 1
 KMC_F_AA, KMC_F_AS = 1, 2

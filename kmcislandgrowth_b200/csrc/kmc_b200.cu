@@ -1079,9 +1079,10 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         if (getenv("KMC_PHASE_TIMING")) {
             const unsigned long long* ph = (const unsigned long long*)(hm + 128);
             const double nls = ds->line_searches > 0 ? (double)ds->line_searches : 1.0;
-            fprintf(stderr, "[kmc2 G detail us/ls] beta-reduce %.2f | rebuild-check %.2f | loads+adatom sweep %.2f | substrate sweep %.2f | group sums %.2f | update+flags %.2f | block max+store %.2f\n", ph[10] / nls * 1e-3, ph[11] / nls * 1e-3, ph[12] / nls * 1e-3, ph[13] / nls * 1e-3, ph[14] / nls * 1e-3, ph[15] / nls * 1e-3, ph[5] / nls * 1e-3);
+            fprintf(stderr, "[kmc2 E detail us/ls] control %.2f | items %.2f | reduce+store %.2f\n", ph[32] / nls * 1e-3, ph[33] / nls * 1e-3, ph[0] / nls * 1e-3);
+            fprintf(stderr, "[kmc2 G detail us/ls] beta-reduce %.2f | rebuild-check %.2f | ranges+copy wait %.2f | adatom sweep %.2f | substrate sweep %.2f | group sums %.2f | update+flags %.2f | block max+store %.2f\n", ph[10] / nls * 1e-3, ph[11] / nls * 1e-3, ph[34] / nls * 1e-3, ph[12] / nls * 1e-3, ph[13] / nls * 1e-3, ph[14] / nls * 1e-3, ph[15] / nls * 1e-3, ph[5] / nls * 1e-3);
             fprintf(stderr, "[kmc2 phase us/ls] E %.2f | bar %.2f | fix+bar %.2f | S %.2f | bar %.2f | G %.2f | bar %.2f | rebuild %.2f (%.1f us each, %lld) movers/ls %.1f (ls=%lld restarts=%lld blocks=%d G=%d items=%d)\n",
-                    ph[0] / nls * 1e-3, ph[1] / nls * 1e-3, ph[2] / nls * 1e-3, ph[3] / nls * 1e-3, ph[4] / nls * 1e-3, (ph[5] + ph[10] + ph[11] + ph[12] + ph[13] + ph[14] + ph[15]) / nls * 1e-3,
+                    (ph[0] + ph[32] + ph[33]) / nls * 1e-3, ph[1] / nls * 1e-3, ph[2] / nls * 1e-3, ph[3] / nls * 1e-3, ph[4] / nls * 1e-3, (ph[5] + ph[34] + ph[10] + ph[11] + ph[12] + ph[13] + ph[14] + ph[15]) / nls * 1e-3,
                     ph[6] / nls * 1e-3, ph[7] / nls * 1e-3, ph[8] ? ph[7] * 1e-3 / ph[8] : 0.0, (long long)ph[8], ph[9] / nls, (long long)ds->line_searches, (long long)ds->restarts, blocks, G, *(const int*)(hm + 20));
         }
         st.line_searches = ds->line_searches; st.restarts = ds->restarts; st.maxF = ds->maxF;

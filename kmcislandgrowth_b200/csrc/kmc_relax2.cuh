@@ -18,7 +18,10 @@
 
 namespace kmc {
 
-constexpr int R2_THREADS = 512;
+#ifndef KMC_R2_THREADS
+#define KMC_R2_THREADS 512
+#endif
+constexpr int R2_THREADS = KMC_R2_THREADS;
 constexpr int R2_NE = KC + PD + 1;  // values reduced per line search: KC per-candidate sums (pairs that are not expanded) + the polynomial
 constexpr int R2_CHUNK = 64;        // pairs per work item
 constexpr int R2_WI = 8;           // work items of a warp cached in shared memory between rebuilds
@@ -91,18 +94,30 @@ __device__ __forceinline__ void relax2_barrier(const Relax2Args& R, unsigned int
 
 constexpr int R2_STAGE = 1024;       // atoms of the neighbourhood staged in shared memory by the force phase (16 KB)
 
+constexpr int R2_NBRC = 80;          // atoms of the block's chunk whose stencil ranges are cached in shared memory
+
 struct Relax2Smem {
     alignas(16) double2 stage[R2_STAGE];     // positions of slots [smin, smax): one TMA 1-D bulk copy per block and line search
+    union {                                  // phase-exclusive scratch
+        struct {                             // force phase: lane partials (adatom / substrate part), summed per atom in lane order
+            double2 fpa[R2_THREADS];
+            double2 fps[R2_THREADS];
+        } g;
+        struct {                             // energy / sums phases, rebuild
+            double wred[R2_THREADS / 32][R2_NE];
+            int scan[R2_THREADS];
+        } e;
+    } u;
+    alignas(16) int4 nbrc[R2_NBRC][4];       // stencil ranges (R.nbr) of the first R2_NBRC atoms of the chunk, valid until the next rebuild
+    WorkItem wit[R2_THREADS / 32][R2_WI];    // this block's warps' first work items (static dealing: valid until the next rebuild)
     alignas(8) unsigned long long mbar;      // mbarrier the bulk copy completes on
     int smin, smax;
-    int scan[R2_THREADS];
-    double wred[R2_THREADS / 32][R2_NE];
-    WorkItem wit[R2_THREADS / 32][R2_WI];    // this block's warps' first work items (static dealing: valid until the next rebuild)
     double e[R2_NE];
     int amin;
     double ctl[4];
     double red[32];
 };
+
 
 // stencil of an in-grid cell (same rule as make_stencil, driven by cell coordinates)
 __device__ __forceinline__ Stencil cell_stencil(const DevParams& P, int cx, int cy) {
@@ -181,15 +196,15 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         const int lo = 1 + t * per, hi = min(lo + per, R.ncell2);
         int sum = 0;
         for (int i = lo; i < hi; ++i) sum += R.start[i];
-        S.scan[t] = sum;
+        S.u.e.scan[t] = sum;
         __syncthreads();
         for (int off = 1; off < T; off <<= 1) {
-            int v = (t >= off) ? S.scan[t - off] : 0;
+            int v = (t >= off) ? S.u.e.scan[t - off] : 0;
             __syncthreads();
-            S.scan[t] += v;
+            S.u.e.scan[t] += v;
             __syncthreads();
         }
-        int run = S.scan[t] - sum;
+        int run = S.u.e.scan[t] - sum;
         for (int i = lo; i < hi; ++i) { run += R.start[i]; R.start[i] = run; }
         __syncthreads();
         for (int i = t; i < R.ncell2; i += T) R.cursor[i] = R.start[i];
@@ -295,17 +310,17 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         const int lo = 1 + t * per, hi = min(lo + per, m + 1);
         int sum = 0;
         for (int i = lo; i < hi; ++i) sum += R.cursor[i];
-        S.scan[t] = sum;
+        S.u.e.scan[t] = sum;
         __syncthreads();
         for (int off = 1; off < T; off <<= 1) {
-            int v = (t >= off) ? S.scan[t - off] : 0;
+            int v = (t >= off) ? S.u.e.scan[t - off] : 0;
             __syncthreads();
-            S.scan[t] += v;
+            S.u.e.scan[t] += v;
             __syncthreads();
         }
-        int run = S.scan[t] - sum;
+        int run = S.u.e.scan[t] - sum;
         for (int i = lo; i < hi; ++i) { run += R.cursor[i]; R.cursor[i] = run; }
-        if (t == T - 1) *R.n_items = S.scan[t];      // true total; the caller checks it against item_cap
+        if (t == T - 1) *R.n_items = S.u.e.scan[t];      // true total; the caller checks it against item_cap
     }
     relax2_barrier(R, epoch);
     for (int c = gtid; c < P.ncell; c += gthreads) {
@@ -464,13 +479,21 @@ __device__ __forceinline__ double relax2_fix_one(const Relax2Args& R, const doub
     return group_sum<32>(e);
 }
 
+// mover test of the next line: 0 only when both ends of the line (a = 0 and a = KC-1; coordinates are monotone in a)
+// lie in the same in-grid cell.  Conservative and division-free: cell coordinates are formed with a reciprocal
+// multiply, and an end closer than 1e-9 cells to a cell wall (or in a negative cell coordinate, where the reference's
+// int() truncates toward zero) makes the atom a mover -- movers are evaluated exactly, per candidate, by the fix-up
+// phase, so a false positive costs time, never accuracy.
 __device__ __forceinline__ uint8_t mover_flag(const DevParams& P, double2 p0, double2 s, double scale) {
-    const double2 pe = cand2(p0, s, KC - 1, scale);
-    int nx0, ny0, nx1, ny1;
-    bin_index(P, p0.x, p0.y, nx0, ny0);
-    bin_index(P, pe.x, pe.y, nx1, ny1);
-    const bool in0 = nx0 >= 0 && nx0 < P.nbx && ny0 >= 0 && ny0 < P.nby;
-    return (in0 && nx0 == nx1 && ny0 == ny1) ? 0 : 1;
+    const double inv_bin = 1.0 / P.bin_size;            // loop invariant: hoisted by the compiler
+    const double k = (double)(KC - 1) / (20.0 * scale) * inv_bin;
+    const double ux0 = (p0.x + P.halfL) * inv_bin, uy0 = (p0.y - P.Dmin) * inv_bin;
+    const double ux1 = fma(s.x, k, ux0), uy1 = fma(s.y, k, uy0);
+    const double fx = floor(ux0), fy = floor(uy0);
+    const double m = 1e-9;
+    const bool same = fmin(ux0, ux1) > fx + m && fmax(ux0, ux1) < fx + 1.0 - m && fmin(uy0, uy1) > fy + m && fmax(uy0, uy1) < fy + 1.0 - m;
+    const bool in0 = fx >= 0.0 && fx < (double)P.nbx && fy >= 0.0 && fy < (double)P.nby;
+    return (same && in0) ? 0 : 1;
 }
 
 // ---- G: forces at `pos` (+ optional fused CG update / mover flags) --------------------------------
@@ -541,17 +564,41 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
 __device__ __forceinline__ void flat_forces(const DevParams& P, const double2* ptr, int4 b, int4 e, int lane, int G, double xi, double yi,
                                             double E, double r0sq, double& fx, double& fy, unsigned long long& visits) {
     const int c0 = e.x - b.x, c1 = c0 + (e.y - b.y), c2 = c1 + (e.z - b.z), tot = c2 + (e.w - b.w);
+    const double E12 = 12.0 * E;
     for (int t = lane; t < tot; t += 8 * G) {
         double2 p[8];
+        bool far = false;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int tk = min(t + k * G, tot - 1);
             const int sl = tk < c0 ? b.x + tk : (tk < c1 ? b.y + (tk - c0) : (tk < c2 ? b.z + (tk - c1) : b.w + (tk - c2)));
             p[k] = ptr[sl];
+            far = far || !(fabs(p[k].x - xi) < P.L);
         }
+        if (far || P.precision == 1) {      // |dx| >= L (atoms that drifted by a box length) or fp32 pair terms: the general form
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (t + k * G < tot) { acc_force(P, xi, yi, p[k], E, r0sq, fx, fy); ++visits; }
+            for (int k = 0; k < 8; ++k)
+                if (t + k * G < tot) { acc_force(P, xi, yi, p[k], E, r0sq, fx, fy); ++visits; }
+        } else {
+            // branch-free: the eight pair chains are independent and interleave (one basic block); a slot past the end
+            // holds a clamped duplicate and contributes a zero coefficient.  Same arithmetic as acc_force.
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                double dx = p[k].x - xi;
+                dx = (dx < 0.0) ? __dadd_rn(dx, P.L) : dx;
+                dx = (dx > P.halfL) ? __dadd_rn(dx, -P.L) : dx;
+                const double dy = p[k].y - yi;
+                const double r2 = dx * dx + dy * dy;
+                const double inv = fast_rcp(r2);
+                const double q2 = r0sq * inv;
+                const double q6 = q2 * q2 * q2;
+                const bool on = (t + k * G < tot) && !(r2 < 1e-4);       // r < 1e-2 skipped (Energy.py:55)
+                const double c = on ? E12 * (q6 - q6 * q6) * inv : 0.0;
+                fx += dx * c;
+                fy += dy * c;
+                visits += (t + k * G < tot) ? 1 : 0;
+            }
+        }
     }
 }
 
@@ -570,6 +617,11 @@ __device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Sm
             const int k = w0 + lane * nw;
             if (k < n_items) S.wit[warp][lane] = R.items[k];
         }
+    }
+    {   // stencil ranges of this block's atoms
+        const int per = (R.n + gridDim.x - 1) / gridDim.x;
+        const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+        for (int i = threadIdx.x; i < 4 * min(hi - lo, R2_NBRC); i += T) S.nbrc[i >> 2][i & 3] = R.nbr[4 * lo + i];
     }
     const int per = (R.n + gridDim.x - 1) / gridDim.x;
     const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
@@ -622,26 +674,36 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
     // its positions are fetched by ONE TMA bulk copy (issued here, or earlier by the caller so that the copy overlaps
     // the control arithmetic) and the sweep reads shared memory.
     const bool staged = smax > smin && (smax - smin) <= R2_STAGE && R.debug != 6;
-    if (staged) {
-        if (issue_here && threadIdx.x == 0) bulk_load(S.stage, pos + smin, (unsigned int)(smax - smin) * 16u, &S.mbar);
-        mbar_wait(&S.mbar, parity);
-        parity ^= 1u;
-    }
+    if (staged && issue_here && threadIdx.x == 0) bulk_load(S.stage, pos + smin, (unsigned int)(smax - smin) * 16u, &S.mbar);
     const double2* npos = staged ? (S.stage - smin) : pos;       // neighbour positions by slot
-    for (int r0 = lo; r0 < hi;) {
-        const int rem = hi - r0;
-        int G = 32;
-        while (G > 1 && (T / G) * 2 < rem) G >>= 1;       // T/G groups must cover >= rem/2
-        const int groups = T / G;
-        const int lane = threadIdx.x & (G - 1);
-        const int slot = r0 + threadIdx.x / G;
-        const bool live = slot < hi;
+    // ONE pass for the block's chunk: every atom gets LPA = T / atoms lanes (7 for 68 atoms on 512 threads; not a power of
+    // two, so the lane partials are summed through shared memory, in lane order: deterministic).  A second, smaller
+    // round for the atoms a power-of-two split leaves over cost a full latency chain on nearly idle SMs.
+    const int cnt = hi - lo;
+    const int LPA = max(1, min(32, T / max(cnt, 1)));
+    const int app = T / LPA;                                  // atoms per pass
+    for (int r0 = lo; r0 < hi; r0 += app) {
+        const int G = LPA;
+        const int grp = threadIdx.x / LPA;
+        const int lane = threadIdx.x - grp * LPA;
+        const int slot = r0 + grp;
+        const bool live = grp < app && slot < hi;
         double ax = 0, ay = 0, sx = 0, sy = 0;
         double2 pi = make_double2(0, 0), so = make_double2(0, 0);
+        int4 ab = make_int4(0, 0, 0, 0), ae = ab, sb = ab, se = ab;
         if (live) {
-            pi = pos[slot];
-            if (lane == 0 && mode == 1) so = sdir[slot];       // fetched together with the position, used by the fused update
-            const int4 ab = R.nbr[4 * slot], ae = R.nbr[4 * slot + 1], sb = R.nbr[4 * slot + 2], se = R.nbr[4 * slot + 3];
+            if (lane == 0 && mode == 1) so = sdir[slot];       // requested now, used by the fused update at the end
+            const int li = slot - lo;
+            if (li < R2_NBRC) { ab = S.nbrc[li][0]; ae = S.nbrc[li][1]; sb = S.nbrc[li][2]; se = S.nbrc[li][3]; }
+            else { ab = R.nbr[4 * slot]; ae = R.nbr[4 * slot + 1]; sb = R.nbr[4 * slot + 2]; se = R.nbr[4 * slot + 3]; }
+        }
+        if (staged && r0 == lo) {       // the copy was issued right after the barrier that published `pos` (or above)
+            mbar_wait(&S.mbar, parity);
+            parity ^= 1u;
+        }
+        GMARK(34)
+        if (live) {
+            pi = (staged && slot >= smin && slot < smax) ? npos[slot] : pos[slot];
             if (ab.x >= 0) {        // stencil ranges cached at the last rebuild
                 if (P.aa_mode == 0) {
                     for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, npos[s], P.E_a, P.ra2, ax, ay);
@@ -661,8 +723,17 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
                 stencil_forces(P, R.sub, st, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
             }
         }
-        ax = group_sum_rt(ax, G); ay = group_sum_rt(ay, G);
-        sx = group_sum_rt(sx, G); sy = group_sum_rt(sy, G);
+        if (r0 != lo) __syncthreads();                          // the previous pass has read its partials
+        S.u.g.fpa[threadIdx.x] = make_double2(ax, ay);
+        S.u.g.fps[threadIdx.x] = make_double2(sx, sy);
+        __syncthreads();
+        if (live && lane == 0) {
+            ax = ay = sx = sy = 0.0;
+            for (int l = 0; l < LPA; ++l) {
+                const double2 a2 = S.u.g.fpa[threadIdx.x + l], s2 = S.u.g.fps[threadIdx.x + l];
+                ax += a2.x; ay += a2.y; sx += s2.x; sy += s2.y;
+            }
+        }
         GMARK(14)
         if (live && lane == 0) {
             const double fx = ax + sx, fy = ay + sy;                // 2DGrowth.py:120
@@ -683,7 +754,6 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
             }
         }
         GMARK(15)
-        r0 += groups;
     }
     if (mode == 1) {
         const double r_mf = block_max(mf, S.red);
@@ -707,6 +777,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     unsigned int epoch = 0;
     unsigned int tma_parity = 0;
     int st_min = 0, st_max = 0;      // staged slot range of this block (relax2_stage_range)
+    int n_items_reg = 0;             // *R.n_items of the last rebuild
     if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
     __syncthreads();
     const DevParams& P = R.P;
@@ -742,24 +813,25 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             const int lo = t * per, hi = min(lo + per, R.n);
             int cnt = 0;
             for (int i = lo; i < hi; ++i) cnt += R.flag[i];
-            S.scan[t] = cnt;
+            S.u.e.scan[t] = cnt;
             __syncthreads();
             for (int off = 1; off < T; off <<= 1) {
-                int v = (t >= off) ? S.scan[t - off] : 0;
+                int v = (t >= off) ? S.u.e.scan[t - off] : 0;
                 __syncthreads();
-                S.scan[t] += v;
+                S.u.e.scan[t] += v;
                 __syncthreads();
             }
-            int p = S.scan[t] - cnt;
+            int p = S.u.e.scan[t] - cnt;
             for (int i = lo; i < hi; ++i)
                 if (R.flag[i]) R.movers[p++] = i;
-            if (t == T - 1) *R.n_movers = S.scan[t];
+            if (t == T - 1) *R.n_movers = S.u.e.scan[t];
         }
         double acc[PD + 1];
 #pragma unroll
         for (int a = 0; a <= PD; ++a) acc[a] = 0.0;
         double eslow = 0.0;                     // lane a < KC: candidate a of the pairs evaluated per candidate
-        const int n_items = *R.n_items;
+        const int n_items = n_items_reg;
+        PHASE2_MARK(32)
         {   // block 0 builds the mover list; when other blocks exist they share the items among themselves
             const int wpb = R2_THREADS / 32;
             const int w0 = nblk > 1 ? gwarp - wpb : gwarp, nw = nblk > 1 ? nwarps - wpb : nwarps;
@@ -782,7 +854,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 }
             }
         }
-        double* wrow = S.wred[warp];            // this warp's row: [0,KC) per-candidate sums, [KC, R2_NE) polynomial
+        PHASE2_MARK(33)
+        double* wrow = S.u.e.wred[warp];            // this warp's row: [0,KC) per-candidate sums, [KC, R2_NE) polynomial
         if (lane < KC) wrow[lane] = eslow;
 #pragma unroll
         for (int a = 0; a <= PD; ++a) {
@@ -792,14 +865,32 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         __syncthreads();
         if (threadIdx.x < R2_NE) {
             double v = 0.0;
-            for (int w = 0; w < R2_THREADS / 32; ++w) v += S.wred[w][threadIdx.x];
+            for (int w = 0; w < R2_THREADS / 32; ++w) v += S.u.e.wred[w][threadIdx.x];
             R.partial[(size_t)threadIdx.x * nblk + blockIdx.x] = v;
         }
         PHASE2_MARK(0)
         relax2_barrier(R, epoch);
         PHASE2_MARK(1)
         // ---------------- F
+        // everything the S phase needs is requested here, in one L2 round trip: the mover count, this thread's atom
+        // (the block's chunk of slots, as in the force phase) and this warp's share of the partial sums
         const int nm = *R.n_movers;
+        const int per = (R.n + nblk - 1) / nblk;
+        const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+        const int myslot = lo + threadIdx.x;
+        double2 pre_p = make_double2(0, 0), pre_s = make_double2(0, 0);
+        unsigned int pre_f = 0;
+        if (myslot < hi) { pre_p = pos[myslot]; pre_s = sdir[myslot]; pre_f = R.flag[myslot]; }
+        constexpr int WPB = R2_THREADS / 32, NEW = (R2_NE + WPB - 1) / WPB;
+        double pv[NEW];
+#pragma unroll
+        for (int i = 0; i < NEW; ++i) {
+            const int a = warp + i * WPB;
+            double v = 0.0;
+            if (a < R2_NE)
+                for (int b = lane; b < nblk; b += 32) v += R.partial[(size_t)a * nblk + b];
+            pv[i] = v;
+        }
         mover_sum += nm;
         if (nm > 0) {
             for (int w = gwarp; w < nm * KC; w += nwarps) {
@@ -810,15 +901,16 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             PHASE2_MARK(2)
         }
         // ---------------- S
-        double2 pre_p = make_double2(0, 0), pre_s = make_double2(0, 0);      // issued ahead of the candidate sums
-        if (gtid < R.n) { pre_p = pos[gtid]; pre_s = sdir[gtid]; }
-        for (int a = warp; a < R2_NE; a += R2_THREADS / 32) {
-            double v = 0.0;
-            for (int b = lane; b < nblk; b += 32) v += R.partial[(size_t)a * nblk + b];
-            if (a < KC)
-                for (int r = lane; r < nm; r += 32) v += R.fix[(size_t)r * KC + a];
-            v = group_sum<32>(v);
-            if (lane == 0) S.e[a] = v;
+#pragma unroll
+        for (int i = 0; i < NEW; ++i) {
+            const int a = warp + i * WPB;
+            if (a < R2_NE) {
+                double v = pv[i];
+                if (a < KC)
+                    for (int r = lane; r < nm; r += 32) v += R.fix[(size_t)r * KC + a];
+                v = group_sum<32>(v);
+                if (lane == 0) S.e[a] = v;
+            }
         }
         __syncthreads();
         if (warp == 0) {        // candidate energies = polynomial + per-candidate sums; first argmin (2DGrowth.py:123,155)
@@ -836,26 +928,31 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         __syncthreads();
         const int amin = S.amin;
         double top = 0.0, bot = 0.0, my = INFINITY;
-        for (int slot = gtid; slot < R.n; slot += gthreads) {
-            const double2 p0 = (slot == gtid) ? pre_p : pos[slot];
-            const double2 p = cand2(p0, (slot == gtid) ? pre_s : sdir[slot], amin, dscale);
+        for (int slot = myslot; slot < hi; slot += R2_THREADS) {
+            const bool first = slot == myslot;
+            const double2 p0 = first ? pre_p : pos[slot];
+            const double2 p = cand2(p0, first ? pre_s : sdir[slot], amin, dscale);
             posn[slot] = p;
             top += p.x * (p.x - p0.x) + p.y * (p.y - p0.y);                // :143
             bot += p0.x * p0.x + p0.y * p0.y;                              // :144
             my = fmin(my, p.y);                                            // :137
-            if (R.flag[slot]) {
+            if (first ? pre_f : (unsigned int)R.flag[slot]) {
                 int nx, ny;
                 bin_index(P, p.x, p.y, nx, ny);
                 if (flat_cell(P, nx, ny) != R.cellof[slot]) *R.need_rebuild = 1;
             }
         }
-        {
-            const double r_top = block_sum(top, S.red);
-            const double r_bot = block_sum(bot, S.red);
-            const double r_my = block_min(my, S.red);
-            if (threadIdx.x == 0) {
-                double* o = R.red + (size_t)blockIdx.x * 4;
-                o[0] = r_top; o[1] = r_bot; o[2] = r_my;
+        {   // one fused block reduction (fixed tree) of the three partials
+            top = group_sum<32>(top); bot = group_sum<32>(bot); my = group_min<32>(my);
+            if (lane == 0) { S.u.e.wred[warp][0] = top; S.u.e.wred[warp][1] = bot; S.u.e.wred[warp][2] = my; }
+            __syncthreads();
+            if (warp == 0) {
+                double t2 = lane < WPB ? S.u.e.wred[lane][0] : 0.0, b2 = lane < WPB ? S.u.e.wred[lane][1] : 0.0, m2 = lane < WPB ? S.u.e.wred[lane][2] : INFINITY;
+                t2 = group_sum<32>(t2); b2 = group_sum<32>(b2); m2 = group_min<32>(m2);
+                if (lane == 0) {
+                    double* o = R.red + (size_t)blockIdx.x * 4;
+                    o[0] = t2; o[1] = b2; o[2] = m2;
+                }
             }
         }
         PHASE2_MARK(3)
@@ -887,6 +984,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             if (*R.n_items > R.item_cap) overflow = true;
             ++rebuilds;
             relax2_stage_range(R, S, st_min, st_max);
+            n_items_reg = *R.n_items;
             PHASE2_MARK(7)
             cs ^= 1;          // the rebuilt x_np now lives in pos[cur]: make it the "next" buffer by flipping cur
             cur ^= 1;
@@ -911,6 +1009,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S);
         if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
         relax2_stage_range(R, S, st_min, st_max);
+        n_items_reg = *R.n_items;
         relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true);   // dx0, sn = dx0  :120,125
         first_pass = false;
         relax2_barrier(R, epoch);
