@@ -403,14 +403,28 @@ __global__ void __launch_bounds__(128) k_probe(DevParams P, const double2* __res
 __global__ void k_select(DevParams P, const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, double u,
                          long long* __restrict__ result, double* __restrict__ rtot, double* __restrict__ pj_out) {
     const int lane = threadIdx.x;
+    // Adding +0.0 never changes a running sum, and the dense table is zero for every non-surface atom: only the
+    // non-zero (or surface-flagged) entries are visited, in index order, so every partial sum keeps the reference's
+    // bits while the chain of dependent additions shrinks from n to the number of surface atoms.  Eight 32-entry
+    // chunks are requested before the first one is consumed (one L2 round trip per 256 entries instead of per 32).
+    constexpr int NB = 8;
     // pass 1: total in reference order
     double sum = 0.0;
-    for (int base = 0; base < n; base += 32) {
-        const double v = (base + lane < n) ? rate[base + lane] : 0.0;
+    for (int base = 0; base < n; base += 32 * NB) {
+        double v[NB];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const double vk = __shfl_sync(0xffffffffu, v, k);
-            sum = __dadd_rn(sum, vk);                       // identical in every lane
+        for (int j = 0; j < NB; ++j) {
+            const int i = base + j * 32 + lane;
+            v[j] = (i < n) ? rate[i] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            unsigned int m = __ballot_sync(0xffffffffu, v[j] != 0.0);
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, v[j], k));      // identical in every lane
+            }
         }
     }
     const double Rtot = __dadd_rn(P.Rd, sum);               // 2DGrowth.py:227
@@ -418,20 +432,46 @@ __global__ void k_select(DevParams P, const double* __restrict__ rate, const uin
     // pass 2: first partial sum > r
     double pj = 0.0;
     int found = -1, kcomp = 0, kfound = -1;
-    if (pj_out && lane == 0) pj_out[0] = 0.0;
-    for (int base = 0; base < n && (found < 0 || pj_out); base += 32) {
-        const double v = (base + lane < n) ? rate[base + lane] : 0.0;
-        const int sf = (base + lane < n) ? (int)surf[base + lane] : 0;
+    if (pj_out) {           // the drop-in API asked for every partial sum (HoppingPartialSums): plain sequential walk
+        if (lane == 0) pj_out[0] = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            const double v = (base + lane < n) ? rate[base + lane] : 0.0;
+            const int sf = (base + lane < n) ? (int)surf[base + lane] : 0;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const double vk = __shfl_sync(0xffffffffu, v, k);
-            const int sk = __shfl_sync(0xffffffffu, sf, k);
-            if (base + k < n) {
-                pj = __dadd_rn(pj, vk);
-                if (pj_out && lane == 0) pj_out[base + k + 1] = pj;
-                if (found < 0 && sk) {
-                    if (pj > r) { found = base + k; kfound = kcomp; }
-                    ++kcomp;
+            for (int k = 0; k < 32; ++k) {
+                const double vk = __shfl_sync(0xffffffffu, v, k);
+                const int sk = __shfl_sync(0xffffffffu, sf, k);
+                if (base + k < n) {
+                    pj = __dadd_rn(pj, vk);
+                    if (lane == 0) pj_out[base + k + 1] = pj;
+                    if (found < 0 && sk) {
+                        if (pj > r) { found = base + k; kfound = kcomp; }
+                        ++kcomp;
+                    }
+                }
+            }
+        }
+    } else {
+        for (int base = 0; base < n && found < 0; base += 32 * NB) {
+            double v[NB];
+            int sf[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int i = base + j * 32 + lane;
+                v[j] = (i < n) ? rate[i] : 0.0;
+                sf[j] = (i < n) ? (int)surf[i] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                unsigned int m = __ballot_sync(0xffffffffu, v[j] != 0.0 || sf[j] != 0);
+                while (m && found < 0) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    pj = __dadd_rn(pj, __shfl_sync(0xffffffffu, v[j], k));
+                    if (__shfl_sync(0xffffffffu, sf[j], k)) {
+                        if (pj > r) { found = base + j * 32 + k; kfound = kcomp; }
+                        ++kcomp;
+                    }
                 }
             }
         }

@@ -112,8 +112,8 @@ __device__ __forceinline__ void pair_line_part(const DevParams& P, double dx0, d
 constexpr int PD = 6;
 constexpr double POLY_UMAX = 3e-3;
 
-// returns false when the pair must take the per-candidate path; inv0 = 1/r0^2
-__device__ __forceinline__ bool pair_line_poly(const DevParams& P, double dx0, double dy0, double ddx, double ddy, double E,
+// returns false when the pair was not expanded (invalid lane, or it must take the per-candidate path); inv0 = 1/r0^2
+__device__ __forceinline__ bool pair_line_poly(const DevParams& P, bool valid, double dx0, double dy0, double ddx, double ddy, double E,
                                                double inv0, double (&acc)[PD + 1]) {
     constexpr double tm = 0.5 * (KC - 1);
     const double mx = fma(tm, ddx, dx0), my = fma(tm, ddy, dy0);      // displacement at the middle of the line
@@ -122,12 +122,14 @@ __device__ __forceinline__ bool pair_line_poly(const DevParams& P, double dx0, d
     const double C = fma(ddx, ddx, ddy * ddy);
     const bool no_wrap = fabs(dx0) + (KC - 1) * fabs(ddx) < P.halfL - 1e-9;
     const bool quiet = fma(C, tm * tm, 2.0 * tm * fabs(Bh)) < POLY_UMAX * A;      // strict: A == 0 is never quiet
-    if (!(no_wrap && quiet)) return false;
-    const double q = fast_rcp(A * inv0);          // r0^2 / A
+    // branch-free: a pair that is not expanded runs the same instructions on harmless operands and adds zeros, so that
+    // the chains of two pairs held by one lane interleave (no basic-block boundary between them)
+    const bool ok = valid && no_wrap && quiet;
+    const double q = fast_rcp(ok ? A * inv0 : 1.0);          // r0^2 / A
     const double w = q * inv0;                    // 1 / A
-    const double b = (Bh + Bh) * w, c = C * w;
+    const double b = ok ? (Bh + Bh) * w : 0.0, c = ok ? C * w : 0.0;
     const double q3 = q * q * q;
-    const double Q3 = E * q3, Q6 = Q3 * q3;
+    const double Q3 = ok ? E * q3 : 0.0, Q6 = Q3 * q3;
     // e(u) = sum_k g_k u^k,  g_k = (-1)^k (C(k+5,5) Q6 - 2 C(k+2,2) Q3)
     const double g0 = fma(1.0, Q6, -2.0 * Q3);
     const double g1 = fma(-6.0, Q6, 6.0 * Q3);
@@ -152,7 +154,7 @@ __device__ __forceinline__ bool pair_line_poly(const DevParams& P, double dx0, d
     acc[2] = fma(b, p1, fma(c, p0, acc[2]));
     acc[1] = fma(b, p0, acc[1]);
     acc[0] += g0;
-    return true;
+    return ok;
 }
 
 // one candidate of one pair, general form (min-image wrap per candidate, r == 0 excluded: Periodic.py:8-20, Energy.py:28)

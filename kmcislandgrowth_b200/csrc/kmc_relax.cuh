@@ -58,14 +58,14 @@ struct RelaxArgs {
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        // arrive with release semantics (cumulative over the block's writes ordered by the bar.sync above), then poll
+        // with acquire loads: no separate membar.gl on either side of the atomic
         const unsigned int target = (epoch + 1u) * gridDim.x;
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
         unsigned int v;
-        do {            // poll in L2 (volatile load: no L1 invalidation per iteration); the fence below is the acquire
-            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < target);
-        __threadfence();
     }
     ++epoch;
     __syncthreads();

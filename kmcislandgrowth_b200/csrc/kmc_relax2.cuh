@@ -18,6 +18,9 @@
 
 namespace kmc {
 
+#ifndef KMC_R2_ILP2
+#define KMC_R2_ILP2 1
+#endif
 #ifndef KMC_R2_THREADS
 #define KMC_R2_THREADS 512
 #endif
@@ -94,6 +97,7 @@ __device__ __forceinline__ void relax2_barrier(const Relax2Args& R, unsigned int
 
 constexpr int R2_STAGE = 1024;       // atoms of the neighbourhood staged in shared memory by the force phase (16 KB)
 
+constexpr int R2_FIX_INLINE = 2;     // up to this many movers are evaluated by block 0 inside the energy phase
 constexpr int R2_NBRC = 80;          // atoms of the block's chunk whose stencil ranges are cached in shared memory
 
 struct Relax2Smem {
@@ -354,13 +358,11 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
 // One pair per lane and round.  Quiet pairs add their Taylor coefficients to acc (pair_line_poly).  Pairs that cannot be
 // expanded are evaluated per candidate by the WARP: each one is broadcast and lane a (< KC) adds candidate a to its private
 // sum `eslow` (fixed order: deterministic; one register instead of KC accumulators per lane).
-__device__ __forceinline__ void relax2_pair_round(const DevParams& P, bool valid, double dx0, double dy0, double ddx, double ddy, bool is_sub,
-                                                  int lane, double (&acc)[PD + 1], double& eslow) {
-    const double E = is_sub ? P.E_as : P.E_a;
-    bool slow = false;
-    if (valid) slow = !pair_line_poly(P, dx0, dy0, ddx, ddy, E, is_sub ? P.inv_ras2 : P.inv_ra2, acc);
+__device__ __forceinline__ void relax2_slow_pairs(const DevParams& P, bool slow, double dx0, double dy0, double ddx, double ddy, bool is_sub,
+                                                  int lane, double& eslow) {
     unsigned int m = __ballot_sync(0xffffffffu, slow);
     if (m) {
+        const double E = is_sub ? P.E_as : P.E_a;
         const double r0sq = is_sub ? P.ras2 : P.ra2;
         while (m) {
             const int src = __ffs(m) - 1;
@@ -370,6 +372,11 @@ __device__ __forceinline__ void relax2_pair_round(const DevParams& P, bool valid
             if (lane < KC) eslow += pair_line_one(P, bx, by, vx, vy, E, r0sq, lane);
         }
     }
+}
+__device__ __forceinline__ void relax2_pair_round(const DevParams& P, bool valid, double dx0, double dy0, double ddx, double ddy, bool is_sub,
+                                                  int lane, double (&acc)[PD + 1], double& eslow) {
+    const bool ok = pair_line_poly(P, valid, dx0, dy0, ddx, ddy, is_sub ? P.E_as : P.E_a, is_sub ? P.inv_ras2 : P.inv_ra2, acc);
+    relax2_slow_pairs(P, valid && !ok, dx0, dy0, ddx, ddy, is_sub, lane, eslow);
 }
 
 // operands of one round of a work item: every load is issued before any of them is used (one L2 round trip), and the
@@ -402,18 +409,35 @@ __device__ __forceinline__ PairLoad relax2_round_load(const Relax2Args& R, const
     L.bits = ((q0 + lane < end) ? 1u : 0u) | (self ? 2u : 0u) | (is_sub ? 4u : 0u) | (fh << 8) | (fj << 16);
     return L;
 }
+struct PairGeo { double dx0, dy0, ddx, ddy; bool valid, is_sub; };
+__device__ __forceinline__ PairGeo relax2_round_geo(const DevParams& P, const PairLoad& L, double inv_step) {
+    PairGeo g;
+    g.is_sub = (L.bits & 4u) != 0;       // warp uniform (a property of the item)
+    // movers are handled by the fix-up phase; pairs inside the home cell count once (slot_i < slot_j)
+    g.valid = (L.bits & 1u) && !(L.bits >> 8) && !((L.bits & 2u) && L.js <= L.hs);
+    g.dx0 = put_in_box(L.pj.x - L.pi.x, P.L, P.halfL);
+    g.dy0 = L.pj.y - L.pi.y;
+    g.ddx = (L.sj.x - L.si.x) * inv_step;
+    g.ddy = (L.sj.y - L.si.y) * inv_step;
+    return g;
+}
 __device__ __forceinline__ void relax2_round_compute(const Relax2Args& R, const PairLoad& L, double inv_step, int lane, double (&acc)[PD + 1], double& eslow) {
     const DevParams& P = R.P;
-    const bool is_sub = (L.bits & 4u) != 0;       // warp uniform (a property of the item)
-    // movers are handled by the fix-up phase; pairs inside the home cell count once (slot_i < slot_j)
-    const bool valid = (L.bits & 1u) && !(L.bits >> 8) && !((L.bits & 2u) && L.js <= L.hs);
-    const double dx0 = put_in_box(L.pj.x - L.pi.x, P.L, P.halfL);
-    const double dy0 = L.pj.y - L.pi.y;
-    const double ddx = (L.sj.x - L.si.x) * inv_step, ddy = (L.sj.y - L.si.y) * inv_step;
-    if (R.debug == 1) { if (valid) acc[0] += dx0 + dy0 + ddx + ddy; return; }
-    relax2_pair_round(P, valid, dx0, dy0, ddx, ddy, is_sub, lane, acc, eslow);
+    const PairGeo g = relax2_round_geo(P, L, inv_step);
+    if (R.debug == 1) { if (g.valid) acc[0] += g.dx0 + g.dy0 + g.ddx + g.ddy; return; }
+    relax2_pair_round(P, g.valid, g.dx0, g.dy0, g.ddx, g.ddy, g.is_sub, lane, acc, eslow);
 }
-
+// two rounds at once: their polynomial chains are independent and interleave
+__device__ __forceinline__ void relax2_round_compute2(const Relax2Args& R, const PairLoad& LA, const PairLoad& LB, double inv_step, int lane,
+                                                      double (&acc)[PD + 1], double& eslow) {
+    const DevParams& P = R.P;
+    const PairGeo ga = relax2_round_geo(P, LA, inv_step), gb = relax2_round_geo(P, LB, inv_step);
+    if (R.debug == 1) { if (ga.valid) acc[0] += ga.dx0 + ga.dy0 + ga.ddx + ga.ddy; if (gb.valid) acc[0] += gb.dx0 + gb.dy0 + gb.ddx + gb.ddy; return; }
+    const bool oka = pair_line_poly(P, ga.valid, ga.dx0, ga.dy0, ga.ddx, ga.ddy, ga.is_sub ? P.E_as : P.E_a, ga.is_sub ? P.inv_ras2 : P.inv_ra2, acc);
+    const bool okb = pair_line_poly(P, gb.valid, gb.dx0, gb.dy0, gb.ddx, gb.ddy, gb.is_sub ? P.E_as : P.E_a, gb.is_sub ? P.inv_ras2 : P.inv_ra2, acc);
+    relax2_slow_pairs(P, ga.valid && !oka, ga.dx0, ga.dy0, ga.ddx, ga.ddy, ga.is_sub, lane, eslow);
+    relax2_slow_pairs(P, gb.valid && !okb, gb.dx0, gb.dy0, gb.ddx, gb.ddy, gb.is_sub, lane, eslow);
+}
 
 // all items k = w0, w0 + nw, ... of this warp; `wit` = the warp's cached copies of the first R2_WI of them
 __device__ __forceinline__ void relax2_items(const Relax2Args& R, const WorkItem* wit, int w0, int nw, int n_items, const double2* pos,
@@ -422,25 +446,42 @@ __device__ __forceinline__ void relax2_items(const Relax2Args& R, const WorkItem
     int idx = 0;                            // ordinal of the current item of this warp
     WorkItem it = wit[0];
     int q0 = it.begin;
-    PairLoad cur = relax2_round_load(R, it, q0, pos, sdir, lane);
-    for (;;) {
-        // advance to the next round
-        bool more = true;
+    // advance (it, q0) to the next round of this warp; false when there is none
+    auto advance = [&]() -> bool {
         q0 += 32;
         if (q0 >= it.begin + it.count) {
             ++idx;
             const int k = w0 + idx * nw;
-            if (k < n_items) {
-                it = (idx < R2_WI) ? wit[idx] : R.items[k];
-                q0 = it.begin;
-            } else more = false;
+            if (k >= n_items) return false;
+            it = (idx < R2_WI) ? wit[idx] : R.items[k];
+            q0 = it.begin;
         }
-        if (!more) break;
+        return true;
+    };
+#if KMC_R2_ILP2
+    // two rounds per step: both sets of operands are requested together (one L2 round trip per two rounds) and their
+    // polynomial chains interleave
+    bool more = true;
+    while (more) {
+        const PairLoad a = relax2_round_load(R, it, q0, pos, sdir, lane);
+        more = advance();
+        if (more) {
+            const PairLoad b = relax2_round_load(R, it, q0, pos, sdir, lane);
+            more = advance();
+            relax2_round_compute2(R, a, b, inv_step, lane, acc, eslow);
+        } else {
+            relax2_round_compute(R, a, inv_step, lane, acc, eslow);
+        }
+    }
+#else
+    PairLoad cur = relax2_round_load(R, it, q0, pos, sdir, lane);
+    while (advance()) {
         const PairLoad nxt = relax2_round_load(R, it, q0, pos, sdir, lane);
         relax2_round_compute(R, cur, inv_step, lane, acc, eslow);
         cur = nxt;
     }
     relax2_round_compute(R, cur, inv_step, lane, acc, eslow);
+#endif
 }
 
 // ---- F: one (mover, candidate) by one warp; sorted-state version of line_fix_one ------------------
@@ -459,9 +500,13 @@ __device__ __forceinline__ double relax2_fix_one(const Relax2Args& R, const doub
     ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = R.n;
     double e = 0.0;
     if (P.aa_mode != 0) {
+        // the partners' candidate positions only enter the pair distance: formed with one FMA (a few 1e-16 relative
+        // from the reference's (a*s)/20/scale); the mover's own position decides its cell and stays exact
+        const double ak = (double)a / (20.0 * scale);
         visit_stencil(P, ad, st, lane, 32, [&](int slot) {
             if (R.flag[slot] || (!in_grid && oidx[slot] < om)) return;
-            const double2 pj = cand2(pos[slot], sdir[slot], a, scale);
+            const double2 p0 = pos[slot], s0 = sdir[slot];
+            const double2 pj = make_double2(fma(s0.x, ak, p0.x), fma(s0.y, ak, p0.y));
             e += pair_energy(P, pm.x, pm.y, pj, P.E_a, P.ra2);
         });
         for (int r2 = lane; r2 < nm; r2 += 32) {               // mover - mover: the lower index sees the higher one
@@ -778,6 +823,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     unsigned int tma_parity = 0;
     int st_min = 0, st_max = 0;      // staged slot range of this block (relax2_stage_range)
     int n_items_reg = 0;             // *R.n_items of the last rebuild
+    bool layout_x0 = false;          // the sorted layout is the one built from x0 and sdir[cs ^ 1] holds F(x0)
     if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
     __syncthreads();
     const DevParams& P = R.P;
@@ -825,6 +871,15 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             for (int i = lo; i < hi; ++i)
                 if (R.flag[i]) R.movers[p++] = i;
             if (t == T - 1) *R.n_movers = S.u.e.scan[t];
+            // a handful of movers: this block (it has no work items) evaluates them right here, which saves the
+            // separate fix-up phase and its grid barrier
+            __syncthreads();
+            const int nm0 = S.u.e.scan[T - 1];
+            if (nblk > 1 && nm0 > 0 && nm0 <= R2_FIX_INLINE)
+                for (int w = warp; w < nm0 * KC; w += R2_THREADS / 32) {
+                    const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane);
+                    if (lane == 0) R.fix[w] = e;
+                }
         }
         double acc[PD + 1];
 #pragma unroll
@@ -892,7 +947,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             pv[i] = v;
         }
         mover_sum += nm;
-        if (nm > 0) {
+        if (nm > (nblk > 1 ? R2_FIX_INLINE : 0)) {
             for (int w = gwarp; w < nm * KC; w += nwarps) {
                 const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane);
                 if (lane == 0) R.fix[w] = e;
@@ -983,6 +1038,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             if (gtid == 0) *R.need_rebuild = 0;
             if (*R.n_items > R.item_cap) overflow = true;
             ++rebuilds;
+            layout_x0 = false;
             relax2_stage_range(R, S, st_min, st_max);
             n_items_reg = *R.n_items;
             PHASE2_MARK(7)
@@ -1006,12 +1062,33 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
 
     for (;;) {                                                         // one pass == one (recursive) call of Relaxation
         if (scale > 1024) { scale = 16; threshold *= 10; }              // :111-113
-        relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S);
-        if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
-        relax2_stage_range(R, S, st_min, st_max);
-        n_items_reg = *R.n_items;
-        relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true);   // dx0, sn = dx0  :120,125
-        first_pass = false;
+        const int per = (R.n + nblk - 1) / nblk;
+        const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+        if (layout_x0) {
+            // restart from the ORIGINAL positions while the sorted layout is still the one built from them: the cell list,
+            // the work items and the first direction dx0 = F(x0) are unchanged (only the mover flags depend on the new
+            // scale), so the pass starts with a gather instead of a rebuild + force sweep
+            const double2* f0 = R.sdir[cs ^ 1];
+            double2* pd = R.pos[cur];
+            double2* sd = R.sdir[cs];
+            const int* oi = R.oidx[cs];
+            for (int slot = lo + threadIdx.x; slot < hi; slot += R2_THREADS) {
+                const double2 p = R.x0[oi[slot]], s0 = f0[slot];
+                pd[slot] = p;
+                sd[slot] = s0;
+                R.flag[slot] = mover_flag(P, p, s0, (double)scale);
+            }
+        } else {
+            relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S);
+            if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
+            relax2_stage_range(R, S, st_min, st_max);
+            n_items_reg = *R.n_items;
+            relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true);   // dx0, sn = dx0  :120,125
+            first_pass = false;
+            __syncthreads();
+            for (int slot = lo + threadIdx.x; slot < hi; slot += R2_THREADS) R.sdir[cs ^ 1][slot] = R.sdir[cs][slot];     // dx0, kept for the restarts
+            layout_x0 = true;
+        }
         relax2_barrier(R, epoch);
         line_search();                                                  // :121-129
         if (overflow) { status = -4; break; }
