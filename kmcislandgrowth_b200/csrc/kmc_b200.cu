@@ -994,11 +994,16 @@ static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
     c->launches++;
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->timing) { cudaEventCreate(&ea); cudaEventCreate(&eb); cudaEventRecord(ea, c->stream); }
+    static bool smem_set = false;        // the kernel's shared state (staged operands) exceeds the 48 KB static limit
+    if (!smem_set) {
+        CK(cudaFuncSetAttribute((const void*)k_relax2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
+        smem_set = true;
+    }
     if (R.sync_mode == 0) {
-        CK(cudaLaunchCooperativeKernel((const void*)k_relax2, dim3(blocks), dim3(R2_THREADS), args, 0, c->stream));
+        CK(cudaLaunchCooperativeKernel((const void*)k_relax2, dim3(blocks), dim3(R2_THREADS), args, sizeof(Relax2Smem), c->stream));
     } else {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(R2_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(R2_THREADS); cfg.dynamicSmemBytes = sizeof(Relax2Smem); cfg.stream = c->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = blocks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1033,7 +1038,7 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         TRY(slot(c, S_OI1, (size_t)n, &R.oidx[1]));
         TRY(slot(c, S_CELLOF, (size_t)n, &R.cellof));
         TRY(slot(c, S_NBR, (size_t)n * 4, &R.nbr));
-        TRY(slot(c, S_FLAG, (size_t)n, &R.flag));
+        TRY(slot(c, S_FLAG, (size_t)n + 32, &R.flag));        // the staged flag copy reads whole 16-byte groups
         TRY(slot(c, S_START, (size_t)R.ncell2, &R.start));
         TRY(slot(c, S_CURSOR, (size_t)R.ncell2, &R.cursor));
         TRY(slot(c, S_KEY, (size_t)n, &R.key));

@@ -37,7 +37,7 @@ struct WorkItem {
     int begin;             // first pair of the chunk in the (home x partner) pair space, pair q = i + nh*j
     int count;             // pairs in the chunk
     float inv_nh;          // 1/nh for the index split
-    int pad;
+    int n2;                // length of the third partner range
 };
 
 struct Relax2Args {
@@ -100,8 +100,16 @@ constexpr int R2_STAGE = 1024;       // atoms of the neighbourhood staged in sha
 constexpr int R2_FIX_INLINE = 2;     // up to this many movers are evaluated by block 0 inside the energy phase
 constexpr int R2_NBRC = 80;          // atoms of the block's chunk whose stencil ranges are cached in shared memory
 
+constexpr int R2_SUBSTAGE = 512;     // substrate atoms cached per block (static between rebuilds)
+
 struct Relax2Smem {
     alignas(16) double2 stage[R2_STAGE];     // positions of slots [smin, smax): one TMA 1-D bulk copy per block and line search
+    // energy phase: operands of this block's work items, slots [emin, emax): positions, directions, mover flags (three
+    // bulk copies completing on mbar_e, requested as soon as the previous line search has published them)
+    alignas(16) double2 epos[R2_STAGE];
+    alignas(16) double2 edir[R2_STAGE];
+    alignas(16) uint8_t eflag[R2_STAGE + 16];
+    alignas(16) double2 esub[R2_SUBSTAGE];   // substrate atoms [submin, submax) of the block's substrate items
     union {                                  // phase-exclusive scratch
         struct {                             // force phase: lane partials (adatom / substrate part), summed per atom in lane order
             double2 fpa[R2_THREADS];
@@ -115,7 +123,9 @@ struct Relax2Smem {
     alignas(16) int4 nbrc[R2_NBRC][4];       // stencil ranges (R.nbr) of the first R2_NBRC atoms of the chunk, valid until the next rebuild
     WorkItem wit[R2_THREADS / 32][R2_WI];    // this block's warps' first work items (static dealing: valid until the next rebuild)
     alignas(8) unsigned long long mbar;      // mbarrier the bulk copy completes on
+    alignas(8) unsigned long long mbar_e;    // mbarrier of the energy-phase copies
     int smin, smax;
+    int emin, emax, submin, submax;
     double e[R2_NE];
     int amin;
     double ctl[4];
@@ -342,7 +352,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
             it.b0 = r.b[0]; it.n0 = r.e[0] - r.b[0]; it.b1 = r.b[1]; it.n1 = r.e[1] - r.b[1]; it.b2 = r.b[2];
             it.kind = r.self[0] | (r.self[1] << 1) | (r.self[2] << 2) | (part >= 4 ? 8 : 0);
             it.inv_nh = 1.0f / (float)nh;
-            it.pad = 0;
+            it.n2 = r.e[2] - r.b[2];
             for (int j = 0; j < cnt; ++j, ++k) {
                 if (k >= R.item_cap) break;
                 it.begin = j * R2_CHUNK;
@@ -386,7 +396,13 @@ struct PairLoad {
     int hs, js;
     unsigned int bits;      // 0: in range, 1: same-cell rule applies, 2: substrate partner, 8..: flag[hs], 16..: flag[js]
 };
-__device__ __forceinline__ PairLoad relax2_round_load(const Relax2Args& R, const WorkItem& it, int q0, const double2* pos, const double2* sdir, int lane) {
+struct EOperands {          // where the energy phase reads from: staged copies (rebased to slot indices) or global memory
+    const double2* pos;
+    const double2* dir;
+    const uint8_t* flag;
+    const double2* sub;
+};
+__device__ __forceinline__ PairLoad relax2_round_load(const EOperands& O, const WorkItem& it, int q0, int lane) {
     PairLoad L;
     const bool is_sub = (it.kind & 8) != 0;
     const int end = it.begin + it.count;
@@ -400,12 +416,12 @@ __device__ __forceinline__ PairLoad relax2_round_load(const Relax2Args& R, const
     else if (j < it.n0 + it.n1) { js = it.b1 + (j - it.n0); self = it.kind & 2; }
     else { js = it.b2 + (j - it.n0 - it.n1); self = it.kind & 4; }
     L.hs = hs; L.js = js;
-    const unsigned int fh = R.flag[hs];
-    const unsigned int fj = is_sub ? 0u : (unsigned int)R.flag[js];
-    L.pi = pos[hs];
-    L.si = sdir[hs];
-    L.pj = is_sub ? R.sub.sxy[js] : pos[js];
-    L.sj = is_sub ? make_double2(0.0, 0.0) : sdir[js];
+    const unsigned int fh = O.flag[hs];
+    const unsigned int fj = is_sub ? 0u : (unsigned int)O.flag[js];
+    L.pi = O.pos[hs];
+    L.si = O.dir[hs];
+    L.pj = is_sub ? O.sub[js] : O.pos[js];
+    L.sj = is_sub ? make_double2(0.0, 0.0) : O.dir[js];
     L.bits = ((q0 + lane < end) ? 1u : 0u) | (self ? 2u : 0u) | (is_sub ? 4u : 0u) | (fh << 8) | (fj << 16);
     return L;
 }
@@ -440,9 +456,10 @@ __device__ __forceinline__ void relax2_round_compute2(const Relax2Args& R, const
 }
 
 // all items k = w0, w0 + nw, ... of this warp; `wit` = the warp's cached copies of the first R2_WI of them
-__device__ __forceinline__ void relax2_items(const Relax2Args& R, const WorkItem* wit, int w0, int nw, int n_items, const double2* pos,
-                                             const double2* sdir, double inv_step, int lane, double (&acc)[PD + 1], double& eslow) {
-    if (w0 < 0 || w0 >= n_items) return;
+// items k = kfirst, kfirst + kstride, ... < kend of this warp; `wit` = the warp's cached copies of the first R2_WI of them
+__device__ __forceinline__ void relax2_items(const Relax2Args& R, const WorkItem* wit, int kfirst, int kstride, int kend, const EOperands& O,
+                                             double inv_step, int lane, double (&acc)[PD + 1], double& eslow) {
+    if (kfirst >= kend) return;
     int idx = 0;                            // ordinal of the current item of this warp
     WorkItem it = wit[0];
     int q0 = it.begin;
@@ -451,37 +468,26 @@ __device__ __forceinline__ void relax2_items(const Relax2Args& R, const WorkItem
         q0 += 32;
         if (q0 >= it.begin + it.count) {
             ++idx;
-            const int k = w0 + idx * nw;
-            if (k >= n_items) return false;
+            const int k = kfirst + idx * kstride;
+            if (k >= kend) return false;
             it = (idx < R2_WI) ? wit[idx] : R.items[k];
             q0 = it.begin;
         }
         return true;
     };
-#if KMC_R2_ILP2
-    // two rounds per step: both sets of operands are requested together (one L2 round trip per two rounds) and their
-    // polynomial chains interleave
+    // two rounds per step: both sets of operands are requested together and their polynomial chains interleave
     bool more = true;
     while (more) {
-        const PairLoad a = relax2_round_load(R, it, q0, pos, sdir, lane);
+        const PairLoad a = relax2_round_load(O, it, q0, lane);
         more = advance();
         if (more) {
-            const PairLoad b = relax2_round_load(R, it, q0, pos, sdir, lane);
+            const PairLoad b = relax2_round_load(O, it, q0, lane);
             more = advance();
             relax2_round_compute2(R, a, b, inv_step, lane, acc, eslow);
         } else {
             relax2_round_compute(R, a, inv_step, lane, acc, eslow);
         }
     }
-#else
-    PairLoad cur = relax2_round_load(R, it, q0, pos, sdir, lane);
-    while (advance()) {
-        const PairLoad nxt = relax2_round_load(R, it, q0, pos, sdir, lane);
-        relax2_round_compute(R, cur, inv_step, lane, acc, eslow);
-        cur = nxt;
-    }
-    relax2_round_compute(R, cur, inv_step, lane, acc, eslow);
-#endif
 }
 
 // ---- F: one (mover, candidate) by one warp; sorted-state version of line_fix_one ------------------
@@ -591,6 +597,18 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsi
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// three copies completing on one mbarrier phase (one arrive.expect_tx for their total size)
+__device__ __forceinline__ void bulk_load3(void* d0, const void* g0, unsigned int n0, void* d1, const void* g1, unsigned int n1,
+                                           void* d2, const void* g2, unsigned int n2, unsigned long long* bar) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(n0 + n1 + n2) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(d0)), "l"(g0), "r"(n0), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(d1)), "l"(g1), "r"(n1), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(d2)), "l"(g2), "r"(n2), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -647,21 +665,56 @@ __device__ __forceinline__ void flat_forces(const DevParams& P, const double2* p
     }
 }
 
+// what the energy phase of a block reads: its contiguous range of work items and, when they fit, the staged operands
+struct ERange {
+    int kb, ke;             // work items [kb, ke) of this block
+    int emin, emax;         // staged slots (emax == emin: not staged, read global memory)
+    int submin, submax;     // cached substrate atoms (submax == submin: read global memory)
+};
+__device__ __forceinline__ void relax2_item_range(const Relax2Args& R, int n_items, int& kb, int& ke) {
+    if (gridDim.x == 1) { kb = 0; ke = n_items; return; }
+    if (blockIdx.x == 0) { kb = ke = 0; return; }          // block 0 builds the mover list instead
+    const long long nb = gridDim.x - 1, b = blockIdx.x - 1;
+    kb = (int)(b * n_items / nb);
+    ke = (int)((b + 1) * n_items / nb);
+}
+
 // Slot range covered by the stencils of this block's chunk of atoms.  The atoms are cell-sorted column-major and only
 // a few cells of a column are occupied, so the stencils of a contiguous chunk cover ONE contiguous slot range (three
 // adjacent columns) except at the periodic seam.  Valid until the next rebuild.
-__device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Smem& S, int& smin, int& smax) {
+__device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Smem& S, int& smin, int& smax, ERange& er) {
     const int T = blockDim.x;
-    {   // cache this warp's first work items (the dealing of the energy phase: item k -> warp k mod nw, block 0 excluded)
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-        const int wpb = blockDim.x >> 5;
-        const int w0 = gridDim.x > 1 ? gwarp - wpb : gwarp, nw = gridDim.x > 1 ? nwarps - wpb : nwarps;
+    {   // the block's work items: a contiguous range of the (home-cell ordered) list, dealt to its warps round robin; the
+        // first R2_WI of every warp are cached.  Contiguous items = adjacent home cells = ONE contiguous slot range of
+        // operands (the same argument as for the force phase), which is what makes the staging below possible.
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
         const int n_items = min(*R.n_items, R.item_cap);
-        if (w0 >= 0 && lane < R2_WI) {
-            const int k = w0 + lane * nw;
-            if (k < n_items) S.wit[warp][lane] = R.items[k];
+        relax2_item_range(R, n_items, er.kb, er.ke);
+        if (lane < R2_WI) {
+            const int k = er.kb + warp + lane * wpb;
+            if (k < er.ke) S.wit[warp][lane] = R.items[k];
         }
+        if (threadIdx.x == 0) { S.emin = 0x7fffffff; S.emax = -1; S.submin = 0x7fffffff; S.submax = -1; }
+        __syncthreads();
+        int mn = 0x7fffffff, mx = -1, smn = 0x7fffffff, smx = -1;
+        for (int k = er.kb + threadIdx.x; k < er.ke; k += T) {
+            const WorkItem it = R.items[k];
+            mn = min(mn, it.hb); mx = max(mx, it.hb + it.nh);
+            int& lo2 = (it.kind & 8) ? smn : mn;
+            int& hi2 = (it.kind & 8) ? smx : mx;
+            if (it.n0 > 0) { lo2 = min(lo2, it.b0); hi2 = max(hi2, it.b0 + it.n0); }
+            if (it.n1 > 0) { lo2 = min(lo2, it.b1); hi2 = max(hi2, it.b1 + it.n1); }
+            if (it.n2 > 0) { lo2 = min(lo2, it.b2); hi2 = max(hi2, it.b2 + it.n2); }
+        }
+        if (mx > mn) { atomicMin(&S.emin, mn); atomicMax(&S.emax, mx); }
+        if (smx > smn) { atomicMin(&S.submin, smn); atomicMax(&S.submax, smx); }
+        __syncthreads();
+        er.emin = S.emin & ~15;               // 16-slot aligned: the flag copy needs a 16-byte aligned source
+        er.emax = S.emax;
+        if (!(er.emax > er.emin && er.emax - er.emin <= R2_STAGE) || R.debug == 6) er.emin = er.emax = 0;
+        er.submin = S.submin; er.submax = S.submax;
+        if (!(er.submax > er.submin && er.submax - er.submin <= R2_SUBSTAGE) || R.debug == 6) er.submin = er.submax = 0;
+        for (int i = er.submin + threadIdx.x; i < er.submax; i += T) S.esub[i - er.submin] = R.sub.sxy[i];      // static: loaded once
     }
     {   // stencil ranges of this block's atoms
         const int per = (R.n + gridDim.x - 1) / gridDim.x;
@@ -818,13 +871,18 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
     }
 
 __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
-    __shared__ Relax2Smem S;
+    extern __shared__ __align__(16) unsigned char r2_smem_raw[];
+    Relax2Smem& S = *reinterpret_cast<Relax2Smem*>(r2_smem_raw);
     unsigned int epoch = 0;
     unsigned int tma_parity = 0;
     int st_min = 0, st_max = 0;      // staged slot range of this block (relax2_stage_range)
     int n_items_reg = 0;             // *R.n_items of the last rebuild
+    ERange er{};                     // work items and staged operands of the energy phase (relax2_stage_range)
+    unsigned int e_parity = 0;
+    bool e_inflight = false;         // copies of the energy-phase operands requested and not yet waited for
+    bool e_fresh = false;            // ... and they are the operands of the NEXT energy phase
     bool layout_x0 = false;          // the sorted layout is the one built from x0 and sdir[cs ^ 1] holds F(x0)
-    if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
+    if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); mbar_init(&S.mbar_e, 1); }
     __syncthreads();
     const DevParams& P = R.P;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
@@ -844,6 +902,15 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     long long rebuilds = 0, mover_sum = 0;
     unsigned long long t_mark = gtimer();
 
+    // request the operands of an energy phase: positions, directions and mover flags of slots [emin, emax)
+    auto issue_e = [&](const double2* p, const double2* d) {
+        if (threadIdx.x == 0) {
+            const unsigned int ne = (unsigned int)(er.emax - er.emin);
+            bulk_load3(S.epos, p + er.emin, ne * 16u, S.edir, d + er.emin, ne * 16u, S.eflag, R.flag + er.emin, (ne + 15u) & ~15u, &S.mbar_e);
+        }
+        e_inflight = true;
+        e_fresh = true;
+    };
     // candidate sums, argmin, x_np, partial reductions; returns after the barrier that publishes x_np
     auto line_search = [&]() {
         const double dscale = (double)scale;
@@ -853,6 +920,10 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         double2* sdir = R.sdir[cs];
         const int* oidx = R.oidx[cs];
         // ---------------- E
+        if (er.emax > er.emin && !e_fresh) {            // first line of a pass: nothing was requested ahead
+            if (e_inflight) { mbar_wait(&S.mbar_e, e_parity); e_parity ^= 1u; }
+            issue_e(pos, sdir);
+        }
         if (blockIdx.x == 0) {          // ordered list of mover slots
             const int T = blockDim.x, t = threadIdx.x;
             const int per = (R.n + T - 1) / T;
@@ -890,7 +961,18 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         {   // block 0 builds the mover list; when other blocks exist they share the items among themselves
             const int wpb = R2_THREADS / 32;
             const int w0 = nblk > 1 ? gwarp - wpb : gwarp, nw = nblk > 1 ? nwarps - wpb : nwarps;
-            if (R.debug != 2) relax2_items(R, S.wit[warp], w0, nw, n_items, pos, sdir, inv_step, lane, acc, eslow);
+            (void)w0; (void)nw; (void)n_items;
+            EOperands O;
+            O.pos = pos; O.dir = sdir; O.flag = R.flag; O.sub = R.sub.sxy;
+            if (er.emax > er.emin) {
+                mbar_wait(&S.mbar_e, e_parity);
+                e_parity ^= 1u;
+                e_inflight = false;
+                e_fresh = false;
+                O.pos = S.epos - er.emin; O.dir = S.edir - er.emin; O.flag = S.eflag - er.emin;
+            }
+            if (er.submax > er.submin) O.sub = S.esub - er.submin;
+            if (R.debug != 2) relax2_items(R, S.wit[warp], er.kb + warp, wpb, er.ke, O, inv_step, lane, acc, eslow);
         }
         if (P.aa_mode == 0) {
             for (int i = gwarp; i < R.n; i += nwarps) {
@@ -1039,7 +1121,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             if (*R.n_items > R.item_cap) overflow = true;
             ++rebuilds;
             layout_x0 = false;
-            relax2_stage_range(R, S, st_min, st_max);
+            relax2_stage_range(R, S, st_min, st_max, er);
             n_items_reg = *R.n_items;
             PHASE2_MARK(7)
             cs ^= 1;          // the rebuilt x_np now lives in pos[cur]: make it the "next" buffer by flipping cur
@@ -1050,6 +1132,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(5)
         relax2_barrier(R, epoch);
         PHASE2_MARK(6)
+        // the next line search (if there is one) starts from x_np with the directions and flags just published: request
+        // its operands now, the copies land while the control arithmetic runs
+        if (er.emax > er.emin) issue_e(R.pos[cur ^ 1], R.sdir[cs]);
         if (threadIdx.x < 32) {
             double mf = 0.0;
             for (int b = lane; b < nblk; b += 32) mf = fmax(mf, R.red[(size_t)b * 4 + 3]);
@@ -1062,6 +1147,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
 
     for (;;) {                                                         // one pass == one (recursive) call of Relaxation
         if (scale > 1024) { scale = 16; threshold *= 10; }              // :111-113
+        e_fresh = false;                                                // the pass rewrites positions, directions and flags
         const int per = (R.n + nblk - 1) / nblk;
         const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
         if (layout_x0) {
@@ -1081,7 +1167,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         } else {
             relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S);
             if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
-            relax2_stage_range(R, S, st_min, st_max);
+            relax2_stage_range(R, S, st_min, st_max, er);
             n_items_reg = *R.n_items;
             relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true);   // dx0, sn = dx0  :120,125
             first_pass = false;
@@ -1109,6 +1195,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         ++restarts;
         scale *= 2;
     }
+    if (e_inflight) mbar_wait(&S.mbar_e, e_parity);                     // no copy may be pending when the block exits
     // result: PutAllInBox(x_np) in the original order   (:166)
     if (status != -4) {
         const double2* posn = R.pos[cur ^ 1];
