@@ -352,15 +352,19 @@ def run_ours(args):
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum of k_relax2 from the committed ncu --set full capture
-                         # (profiles/r1d_relax2_ncu.md, revision g: 0.852 MB for a 200-line-search launch), scaled to this run's
+                         # (profiles/r1m_relax2_ncu.md: 1.635 MB for a 200-line-search launch), scaled to this run's
                          # line searches per launch: the working set is L2 resident, DRAM sees first touches only
-                         "traffic": 852224.0 / 200.0 * ls_mean, "traffic_source": "profiles/r1d_relax2_ncu.md (4.26 kB per line search)",
+                         "traffic": 1634816.0 / 200.0 * ls_mean, "traffic_source": "profiles/r1m_relax2_ncu.md (8.2 kB per line search)",
                          "algorithmic_bytes_per_launch": abytes, "bytes_detail": binfo,
                          "avg_launch_us": k_ms * 1e3, "launches": ek["launches"],
                          "kernel_share_of_gpu_time": ek["ms"] / total_kernel_ms if total_kernel_ms else None,
                          "binding_roof": "fp64 pipe (about 80 flop per algorithmic byte, SURVEY.md §8d)",
                          "algorithmic_bytes_per_line_search": abytes_line + abytes_force,
-                         "fp64_gflops": ((10 + 14 * 20) * pr["energy"] + 24 * pr["forces"]) * ls_mean / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0},
+                         # flops the reference's formulation spends on the same work (10 + 14 per candidate per energy pair, 24 per
+                         # force pair) / kernel time, and the flops this kernel actually issues: the 20 candidates of a
+                         # pair are ONE degree-6 polynomial (~91 FP64 instructions, FMA = 2 flops) instead of 20 evaluations
+                         "fp64_gflops_reference_formulation": ((10 + 14 * 20) * pr["energy"] + 24 * pr["forces"]) * ls_mean / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
+                         "fp64_gflops_issued": (2 * 91 * pr["energy"] + 2 * 26 * pr["forces"]) * ls_mean / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0},
             "kernel_families_ms": {k: round(v["ms"], 3) for k, v in fam.items()},
             "cpu_baseline": cpu,
             "prerelax": {"line_searches": int(st.line_searches), "status": int(st.status)},

@@ -26,8 +26,11 @@ namespace kmc {
 #endif
 constexpr int R2_THREADS = KMC_R2_THREADS;
 constexpr int R2_NE = KC + PD + 1;  // values reduced per line search: KC per-candidate sums (pairs that are not expanded) + the polynomial
-constexpr int R2_CHUNK = 64;        // pairs per work item
-constexpr int R2_WI = 8;           // work items of a warp cached in shared memory between rebuilds
+#ifndef KMC_R2_CHUNK
+#define KMC_R2_CHUNK 64
+#endif
+constexpr int R2_CHUNK = KMC_R2_CHUNK;        // pairs per work item
+constexpr int R2_WI = 12;          // work items of a warp cached in shared memory between rebuilds
 constexpr int R2_PARTS = 8;         // per home cell: adatom columns 0..3, substrate columns 0..3
 
 struct WorkItem {
@@ -772,7 +775,11 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
     // its positions are fetched by ONE TMA bulk copy (issued here, or earlier by the caller so that the copy overlaps
     // the control arithmetic) and the sweep reads shared memory.
     const bool staged = smax > smin && (smax - smin) <= R2_STAGE && R.debug != 6;
-    if (staged && issue_here && threadIdx.x == 0) bulk_load(S.stage, pos + smin, (unsigned int)(smax - smin) * 16u, &S.mbar);
+    if (staged && issue_here) {          // not loaded ahead by the caller (first sweep of a pass, after a rebuild)
+        __syncthreads();
+        for (int i = threadIdx.x; i < smax - smin; i += T) S.stage[i] = pos[smin + i];
+        __syncthreads();
+    }
     const double2* npos = staged ? (S.stage - smin) : pos;       // neighbour positions by slot
     // ONE pass for the block's chunk: every atom gets LPA = T / atoms lanes (7 for 68 atoms on 512 threads; not a power of
     // two, so the lane partials are summed through shared memory, in lane order: deterministic).  A second, smaller
@@ -794,10 +801,6 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
             const int li = slot - lo;
             if (li < R2_NBRC) { ab = S.nbrc[li][0]; ae = S.nbrc[li][1]; sb = S.nbrc[li][2]; se = S.nbrc[li][3]; }
             else { ab = R.nbr[4 * slot]; ae = R.nbr[4 * slot + 1]; sb = R.nbr[4 * slot + 2]; se = R.nbr[4 * slot + 3]; }
-        }
-        if (staged && r0 == lo) {       // the copy was issued right after the barrier that published `pos` (or above)
-            mbar_wait(&S.mbar, parity);
-            parity ^= 1u;
         }
         GMARK(34)
         if (live) {
@@ -1095,26 +1098,41 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(3)
         relax2_barrier(R, epoch);
         PHASE2_MARK(4)
-        // x_np is published: start the TMA copy of this block's neighbourhood now, it lands while beta is being formed
+        // x_np is published: fetch this block's neighbourhood [st_min, st_max) (two elements per thread) together with
+        // the beta partials -- ONE L2 round trip, one __syncthreads -- into shared memory for the force sweep.
+        // (A TMA bulk copy of the same ~5 KB took ~1.9 us from issue to completion here; plain loads take ~0.7 us.)
         const bool early = st_max > st_min && R.debug != 6;
-        if (early && threadIdx.x == 0) bulk_load(S.stage, posn + st_min, (unsigned int)(st_max - st_min) * 16u, &S.mbar);
-        // every block: beta and min-y from the same partials in the same order
-        if (threadIdx.x < 32) {
-            double t2 = 0.0, b2 = 0.0, m2 = INFINITY;
-            for (int b = lane; b < nblk; b += 32) {
-                const double* o = R.red + (size_t)b * 4;
-                t2 += o[0]; b2 += o[1]; m2 = fmin(m2, o[2]);
+        const int rebuild_now = *R.need_rebuild;             // requested with the rest
+        {
+            const int scnt = st_max - st_min;
+            double2 sv[R2_STAGE / R2_THREADS];
+#pragma unroll
+            for (int k = 0; k < R2_STAGE / R2_THREADS; ++k) {
+                const int i = threadIdx.x + k * R2_THREADS;
+                sv[k] = (early && i < scnt) ? posn[st_min + i] : make_double2(0.0, 0.0);
             }
-            t2 = group_sum<32>(t2); b2 = group_sum<32>(b2); m2 = group_min<32>(m2);
-            if (lane == 0) { S.ctl[0] = t2; S.ctl[1] = b2; S.ctl[2] = m2; }
+            // every block: beta and min-y from the same partials in the same order
+            if (threadIdx.x < 32) {
+                double t2 = 0.0, b2 = 0.0, m2 = INFINITY;
+                for (int b = lane; b < nblk; b += 32) {
+                    const double* o = R.red + (size_t)b * 4;
+                    t2 += o[0]; b2 += o[1]; m2 = fmin(m2, o[2]);
+                }
+                t2 = group_sum<32>(t2); b2 = group_sum<32>(b2); m2 = group_min<32>(m2);
+                if (lane == 0) { S.ctl[0] = t2; S.ctl[1] = b2; S.ctl[2] = m2; }
+            }
+#pragma unroll
+            for (int k = 0; k < R2_STAGE / R2_THREADS; ++k) {
+                const int i = threadIdx.x + k * R2_THREADS;
+                if (early && i < scnt) S.stage[i] = sv[k];
+            }
         }
         __syncthreads();
         const double beta = S.ctl[0] / S.ctl[1];                          // :143-145
         PHASE2_MARK(10)
         // ---------------- rebuild (rare) + G
         bool issue_here = false;
-        if (*R.need_rebuild) {
-            if (early) { mbar_wait(&S.mbar, tma_parity); tma_parity ^= 1u; }      // retire the copy of the stale order
+        if (rebuild_now) {
             issue_here = true;
             relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S);
             if (gtid == 0) *R.need_rebuild = 0;
