@@ -361,6 +361,51 @@ def test_relaxation_engines_agree(W, Hs, Ha, n, aa, cap):
     assert np.max(np.abs(res[2][0] - res[0][0])) < 1e-9 and np.max(np.abs(res[1][0] - res[0][0])) < 1e-9
 
 
+def test_staged_operands_are_bit_identical_to_global_reads(monkeypatch):
+    """k_relax2 reads the operands of the energy and force phases from shared-memory copies (TMA bulk copies / cached
+    substrate atoms); KMC_DEBUG_E=6 makes it read global memory instead.  Where the operands come from must not change
+    a single bit of the result: same line searches, same restarts, identical positions."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(64, 16, 16, aa_mode=1)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, 1500, seed=77, sigma=0.05)
+    out = {}
+    for dbg in ("0", "6"):
+        monkeypatch.setenv("KMC_DEBUG_E", dbg)
+        ctx = runtime.Context(runtime.params_from(gv), 0)
+        sb = ctx.bins_create(sub)
+        ctx.state_set(ad)
+        st = ctx.relax(sb, 16, 1e-4, 150)
+        out[dbg] = (ctx.state_get().copy(), int(st.line_searches), int(st.restarts), float(st.maxF))
+        sb.close()
+        ctx.close()
+    assert out["0"][1:] == out["6"][1:]
+    assert np.array_equal(out["0"][0], out["6"][0])
+
+
+def test_line_polynomial_and_per_candidate_paths_against_oracle():
+    """The line-search energy is summed as per-pair Taylor polynomials for pairs that move little and per candidate for
+    the others (kmc_line.cuh: pair_line_poly / pair_line_one).  A film with one strongly displaced atom makes the first
+    line searches of the relaxation use BOTH paths (displacements from 1e-6 to 0.3 A along one line); the trajectory must
+    follow the oracle: same line-search and restart counts, positions to 1e-7."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(48, 12, 12, aa_mode=1)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, 600, seed=11, sigma=0.01)
+    ad = ad.copy()
+    ad[2 * 300] += 0.45          # one atom pushed far out of its site: eV/A forces on it and its neighbours
+    ad[2 * 300 + 1] += 0.35
+    o = _oracle_for(gv)
+    xo, sto, rc = o.Relaxation(ad, o.PutInBins(sub), max_line_searches=120)
+    ctx = runtime.Context(runtime.params_from(gv), 0)
+    sb = ctx.bins_create(sub)
+    ctx.state_set(ad)
+    st = ctx.relax(sb, 16, 1e-4, 120)
+    x = ctx.state_get()
+    sb.close()
+    ctx.close()
+    assert (int(st.line_searches), int(st.restarts)) == (int(sto.line_searches), int(sto.restarts))
+    assert np.max(np.abs(x - xo)) < 1e-7
+
+
 def test_checkpoint_and_island_statistics(tmp_path):
     """Simulation.save / load round trip, the KMC clock extension, and island statistics of a GPU trajectory equal to
     those of the reference's trajectory (same uniforms -> same states -> same observables)."""
