@@ -1055,6 +1055,7 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         CK(cudaMemsetAsync(sync, 0, 512, c->stream));
         R.barrier = (unsigned int*)sync;
         R.hist = (unsigned long long*)(sync + 256);
+        R.blk_ns = nullptr;
         R.need_rebuild = (int*)(sync + 16);
         R.n_items = (int*)(sync + 20);
         R.n_movers = (int*)(sync + 24);
@@ -1065,7 +1066,23 @@ static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         R.sync_mode = sync_mode;
         R.debug = getenv("KMC_DEBUG_E") ? atoi(getenv("KMC_DEBUG_E")) : 0;
         R.phase_block = !getenv("KMC_PHASE_TIMING") ? -1 : (getenv("KMC_PHASE_BLOCK") ? std::min(atoi(getenv("KMC_PHASE_BLOCK")), blocks - 1) : 0);
+        if (R.debug == 8) {      // diagnostics: per-block phase times (borrows the mover fix-up buffer's tail: n*KC doubles >> 2*blocks)
+            TRY(slot(c, S_TMP3, (size_t)2 * blocks, &R.blk_ns));
+            CK(cudaMemsetAsync(R.blk_ns, 0, sizeof(unsigned long long) * 2 * blocks, c->stream));
+        }
         TRY(launch_relax2(c, R, blocks));
+        if (R.debug == 8) {
+            std::vector<unsigned long long> h(2 * blocks);
+            CK(cudaMemcpyAsync(h.data(), R.blk_ns, sizeof(unsigned long long) * 2 * blocks, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (int ph = 0; ph < 2; ++ph) {
+                double mn = 1e30, mx = 0, sum = 0; int arg = 0;
+                for (int b = (blocks > 1 ? 1 : 0); b < blocks; ++b) { const double v = (double)h[2 * b + ph]; sum += v; if (v < mn) mn = v; if (v > mx) { mx = v; arg = b; } }
+                fprintf(stderr, "[kmc2 per-block %s ns total] min %.0f mean %.0f max %.0f (block %d) block0 %.0f :", ph ? "G" : "E", mn, sum / std::max(1, blocks - 1), mx, arg, (double)h[ph]);
+                for (int b = 0; b < blocks; b += 7) fprintf(stderr, " %.0f", (double)h[2 * b + ph] * 1e-3);
+                fprintf(stderr, "\n");
+            }
+        }
         TRY(mail(c, sync, 512));
         const char* hm = (const char*)c->h_mail;
         if (R.debug == 7) {     // diagnostics: per-atom displacement over a whole line (19/20/scale*|s|), decades from 1e-6 A

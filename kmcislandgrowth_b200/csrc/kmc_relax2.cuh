@@ -78,6 +78,7 @@ struct Relax2Args {
     KmcRelaxStatsDev* stats;
     unsigned long long* phase_ns;
     unsigned long long* hist;   // diagnostics (debug == 7): histogram of per-atom line displacements
+    unsigned long long* blk_ns; // diagnostics (debug == 8): [gridDim][2] time every block spends in the energy / force phase
     int phase_block;        // which block's thread 0 keeps the phase timers (diagnostics)
     int sync_mode;          // 0: global atomic barrier (cooperative launch), 1: one block (__syncthreads), 2: one thread-block cluster (hardware barrier)
     int debug;              // diagnostics only: 1 = energy phase skips the pair arithmetic, 2 = skips the work items
@@ -923,6 +924,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         double2* sdir = R.sdir[cs];
         const int* oidx = R.oidx[cs];
         // ---------------- E
+        unsigned long long t_blk = (R.debug == 8 && threadIdx.x == 0) ? gtimer() : 0ull;
         if (er.emax > er.emin && !e_fresh) {            // first line of a pass: nothing was requested ahead
             if (e_inflight) { mbar_wait(&S.mbar_e, e_parity); e_parity ^= 1u; }
             issue_e(pos, sdir);
@@ -1009,6 +1011,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             R.partial[(size_t)threadIdx.x * nblk + blockIdx.x] = v;
         }
         PHASE2_MARK(0)
+        if (R.debug == 8 && threadIdx.x == 0) R.blk_ns[2 * blockIdx.x] += gtimer() - t_blk;
         relax2_barrier(R, epoch);
         PHASE2_MARK(1)
         // ---------------- F
@@ -1098,6 +1101,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(3)
         relax2_barrier(R, epoch);
         PHASE2_MARK(4)
+        if (R.debug == 8 && threadIdx.x == 0) t_blk = gtimer();
         // x_np is published: fetch this block's neighbourhood [st_min, st_max) (two elements per thread) together with
         // the beta partials -- ONE L2 round trip, one __syncthreads -- into shared memory for the force sweep.
         // (A TMA bulk copy of the same ~5 KB took ~1.9 us from issue to completion here; plain loads take ~0.7 us.)
@@ -1148,6 +1152,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(11)
         relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, tma_parity, st_min, st_max, issue_here, &t_mark);
         PHASE2_MARK(5)
+        if (R.debug == 8 && threadIdx.x == 0) R.blk_ns[2 * blockIdx.x + 1] += gtimer() - t_blk;
         relax2_barrier(R, epoch);
         PHASE2_MARK(6)
         // the next line search (if there is one) starts from x_np with the directions and flags just published: request
