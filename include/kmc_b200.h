@@ -162,7 +162,20 @@ int kmc_set_select_mode(KmcCtx* ctx, int mode);
 /* upload / download the adatom array of the context's trajectory (capacity grows on demand) */
 int kmc_state_set(KmcCtx* ctx, const double* xy, int64_t n, int mem);
 int kmc_state_get(KmcCtx* ctx, double* xy, int64_t cap_atoms, int64_t* n_out, int mem);
+/* new positions for the SAME atoms (n must equal the state's count): unlike kmc_state_set this keeps the history of the
+ * incremental rate table, i.e. the next kmc_rates_update redoes only what these moves touched */
+int kmc_state_move(KmcCtx* ctx, const double* xy, int64_t n, int mem);
 int64_t kmc_state_count(KmcCtx* ctx);
+/* Incremental rate table of the resident trajectory (north star item 3; the reference rebuilds the whole list on every
+ * event, 2DGrowth.py:201-215,318).  The context remembers, per adatom, the rate / surface flag / barrier and the position
+ * they were computed at; an update recomputes only the adatoms of cells whose 3x3(+seam) stencil (Bins.py:44-70) holds an
+ * atom that moved by more than `threshold` Angstrom since then, was added (DepositAdatom :93, HopAtom :255) or removed
+ * (HopAtom :241 -- the cached entries follow the index shift).  threshold = 0 reproduces the full sweep bit for bit;
+ * all-pairs adatom sums (aa_mode 0) always fall back to the full sweep.  Outputs are dense, like kmc_rates; any may be NULL.
+ * kmc_set_rate_mode(ctx, 1, threshold) makes kmc_event use the incremental table (default 0: full sweep). */
+int kmc_rates_update(KmcCtx* ctx, const KmcBins* sbins, double threshold, double* rate_dense, uint8_t* is_surface, double* delta_u,
+                     int64_t* n_recomputed, int mem);
+int kmc_set_rate_mode(KmcCtx* ctx, int mode, double threshold);
 /* 2DGrowth.py:97-166 Relaxation(adatoms, substrate_bins, scale=16, threshold=1e-4) of the trajectory state:
  * 20-point line search + pseudo-CG + the reference's restart logic.  max_line_searches <= 0: no cap. */
 int kmc_relax(KmcCtx* ctx, const KmcBins* sbins, int32_t scale0, double threshold0, int64_t max_line_searches, KmcRelaxStats* stats);

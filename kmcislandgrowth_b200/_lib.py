@@ -71,11 +71,14 @@ SIGNATURES = {
     "kmc_rates": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int]),
     "kmc_select": (C.c_int, [_VP, _VP, _VP, _I64, _D, _VP, _VP, _VP, C.c_int]),
     "kmc_state_set": (C.c_int, [_VP, _VP, _I64, C.c_int]),
+    "kmc_state_move": (C.c_int, [_VP, _VP, _I64, C.c_int]),
     "kmc_state_get": (C.c_int, [_VP, _VP, _I64, C.POINTER(_I64), C.c_int]),
     "kmc_state_count": (_I64, [_VP]),
     "kmc_relax": (C.c_int, [_VP, _VP, _I32, _D, _I64, C.POINTER(KmcRelaxStats)]),
     "kmc_set_relax_mode": (C.c_int, [_VP, C.c_int]),
     "kmc_set_select_mode": (C.c_int, [_VP, C.c_int]),
+    "kmc_set_rate_mode": (C.c_int, [_VP, C.c_int, _D]),
+    "kmc_rates_update": (C.c_int, [_VP, _VP, _D, _VP, _VP, _VP, C.POINTER(_I64), C.c_int]),
     "kmc_deposit_place": (C.c_int, [_VP, _VP, _D]),
     "kmc_hop_place": (C.c_int, [_VP, _VP, _I64, _D]),
     "kmc_event": (C.c_int, [_VP, _VP, _D, _D, _I64, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_D),

@@ -80,6 +80,17 @@ struct KmcCtx {
     int64_t st_n = 0, st_cap = 0;
     int relax_mode = 2;             // 2: persistent kernel on cell-sorted state (default), 1: first-generation persistent kernel, 0: host-driven loop
     size_t item_cap = 0;
+    // incremental rate table (kmc_rates_update): cached per-atom results and the positions they were computed at
+    int rate_mode = 0;              // 0: full sweep per event (default, parity mode); 1: kmc_event uses kmc_rates_update
+    double rate_threshold = 0.0;    // displacement (Angstrom) below which a neighbourhood counts as unchanged; 0 = exact
+    double2* rc_xy = nullptr;
+    double* rc_rate = nullptr;
+    double* rc_du = nullptr;
+    uint8_t* rc_surf = nullptr;
+    double2* rc_pending = nullptr;  // positions of removed atoms whose neighbourhood must be refreshed
+    int rc_npending = 0;
+    int64_t rc_cap = 0, rc_n = 0, rc_last = 0;
+    bool rc_valid = false;
     int select_mode = 0;            // 0: sequential-order sums up to 65536 atoms, block scan beyond; 1: always sequential; 2: always block scan
     int sm_count = 148;
 };
@@ -361,6 +372,111 @@ static int rates_dev(KmcCtx* c, const double2* d_xy, int n, const KmcBins* sb, d
     return 0;
 }
 
+// ---- incremental rate table ------------------------------------------------------------------------------
+constexpr int RC_PENDING = 64;
+static int mail(KmcCtx* c, const void* dev, size_t bytes);
+static int rc_reserve(KmcCtx* c, int64_t n) {
+    if (n <= c->rc_cap && c->rc_xy) return 0;
+    const int64_t cap = std::max<int64_t>(n + n / 2, 1024);
+    double2* xy; double* rate; double* du; uint8_t* surf;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMalloc(&xy, sizeof(double2) * (size_t)cap));
+    CK(cudaMalloc(&rate, sizeof(double) * (size_t)cap));
+    CK(cudaMalloc(&du, sizeof(double) * (size_t)cap));
+    CK(cudaMalloc(&surf, (size_t)cap));
+    if (c->rc_xy) {
+        CK(cudaMemcpy(xy, c->rc_xy, sizeof(double2) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(rate, c->rc_rate, sizeof(double) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(du, c->rc_du, sizeof(double) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(surf, c->rc_surf, (size_t)c->rc_n, cudaMemcpyDeviceToDevice));
+        cudaFree(c->rc_xy); cudaFree(c->rc_rate); cudaFree(c->rc_du); cudaFree(c->rc_surf);
+    }
+    if (!c->rc_pending) CK(cudaMalloc(&c->rc_pending, sizeof(double2) * RC_PENDING));
+    c->rc_xy = xy; c->rc_rate = rate; c->rc_du = du; c->rc_surf = surf; c->rc_cap = cap;
+    return 0;
+}
+
+// the cached tables follow the index changes of the trajectory state: HopAtom deletes entry k and appends the moved atom
+// (2DGrowth.py:241,255), DepositAdatom appends (:93).  A new atom has no cached entry (NaN reference position).
+static int rc_on_remove(KmcCtx* c, int k) {
+    if (!c->rc_valid) return 0;
+    const int n = (int)c->rc_n;
+    if (c->rc_npending >= RC_PENDING) { c->rc_valid = false; return 0; }
+    CK(cudaMemcpyAsync(c->rc_pending + c->rc_npending, c->st_xy + 2 * (size_t)k, sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+    c->rc_npending++;
+    double2* t2; double* t1; uint8_t* t0;
+    TRY(slot(c, S_IN1, (size_t)n, &t2));
+    LAUNCH(c, "misc_erase", k_erase_at<double2>, cdiv(n, 256), 256, (const double2*)c->rc_xy, n, k, t2);
+    CK(cudaMemcpyAsync(c->rc_xy, t2, sizeof(double2) * (size_t)(n - 1), cudaMemcpyDeviceToDevice, c->stream));
+    TRY(slot(c, S_IN2, (size_t)n, &t1));
+    LAUNCH(c, "misc_erase", k_erase_at<double>, cdiv(n, 256), 256, (const double*)c->rc_rate, n, k, t1);
+    CK(cudaMemcpyAsync(c->rc_rate, t1, sizeof(double) * (size_t)(n - 1), cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH(c, "misc_erase", k_erase_at<double>, cdiv(n, 256), 256, (const double*)c->rc_du, n, k, t1);
+    CK(cudaMemcpyAsync(c->rc_du, t1, sizeof(double) * (size_t)(n - 1), cudaMemcpyDeviceToDevice, c->stream));
+    TRY(slot(c, S_IN3, (size_t)n, &t0));
+    LAUNCH(c, "misc_erase", k_erase_at<uint8_t>, cdiv(n, 256), 256, (const uint8_t*)c->rc_surf, n, k, t0);
+    CK(cudaMemcpyAsync(c->rc_surf, t0, (size_t)(n - 1), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaGetLastError());
+    c->rc_n = n - 1;
+    return 0;
+}
+static int rc_on_append(KmcCtx* c) {
+    if (!c->rc_valid) return 0;
+    TRY(rc_reserve(c, c->rc_n + 1));
+    const double nan2[2] = {std::nan(""), std::nan("")};
+    CK(cudaMemcpyAsync(c->rc_xy + c->rc_n, nan2, sizeof(nan2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));       // nan2 lives on the stack
+    c->rc_n++;
+    return 0;
+}
+
+// bring the cached rate table up to date with the trajectory state; returns the number of atoms recomputed
+static int rates_update_impl(KmcCtx* c, const KmcBins* sb, double threshold, int64_t* recomputed) {
+    const int n = (int)c->st_n;
+    *recomputed = 0;
+    if (n == 0) { c->rc_n = 0; c->rc_valid = true; c->rc_npending = 0; return 0; }
+    TRY(rc_reserve(c, n));
+    const bool full = !c->rc_valid || c->rc_n != n || c->dp.aa_mode == 0;      // all-pairs U_appx: every rate depends on every atom
+    if (full) {
+        TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, c->rc_rate, c->rc_surf, c->rc_du, nullptr, nullptr, nullptr, nullptr));
+        CK(cudaMemcpyAsync(c->rc_xy, c->st_xy, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+        c->rc_n = n; c->rc_valid = true; c->rc_npending = 0;
+        *recomputed = n;
+        c->rc_last = n;
+        return 0;
+    }
+    uint8_t *dirty_cell, *self_dirty;
+    unsigned long long* counter;
+    TRY(slot(c, S_OUT4, (size_t)c->dp.ncell + 16, &dirty_cell));
+    TRY(slot(c, S_OUT5, (size_t)n, &self_dirty));
+    TRY(slot(c, S_OUT6, 1, &counter));
+    CK(cudaMemsetAsync(dirty_cell, 0, (size_t)c->dp.ncell + 16, c->stream));
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
+    LAUNCH(c, "rates_mark", k_rates_mark, cdiv(std::max(n, c->rc_npending), 256), 256, c->dp, (const double2*)c->st_xy, (const double2*)c->rc_xy, n,
+           threshold * threshold, (const double2*)c->rc_pending, c->rc_npending, dirty_cell, self_dirty);
+    CellView ad;
+    TRY(scratch_cells(c, (const double2*)c->st_xy, n, 1, &ad));
+    const int G = pick_group(n);
+    const unsigned grid = cdiv((size_t)n * G, 256);
+    CellView sub = view_of(sb);
+    double* nd = nullptr; int* ni = nullptr;
+#define RATES_MASKED(GG) LAUNCH(c, "sweep_rates", k_sweep_rates<GG>, grid, 256, c->dp, ad, sub, n, c->rc_rate, c->rc_surf, c->rc_du, nd, nd, ni, ni, \
+                                (const uint8_t*)dirty_cell, (const uint8_t*)self_dirty, c->rc_xy, counter)
+    switch (G) {
+        case 32: RATES_MASKED(32); break;
+        case 16: RATES_MASKED(16); break;
+        case 8: RATES_MASKED(8); break;
+        default: RATES_MASKED(4); break;
+    }
+#undef RATES_MASKED
+    CK(cudaGetLastError());
+    TRY(mail(c, counter, sizeof(unsigned long long)));
+    *recomputed = (int64_t) * (const unsigned long long*)c->h_mail;
+    c->rc_last = *recomputed;
+    c->rc_npending = 0;
+    return 0;
+}
+
 static int state_reserve(KmcCtx* c, int64_t n) {
     if (n <= c->st_cap) return 0;
     int64_t cap = std::max<int64_t>(n + n / 2, 1024);
@@ -426,6 +542,8 @@ int kmc_destroy(KmcCtx* c) {
     for (auto& b : c->slots) if (b.p) cudaFree(b.p);
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->st_xy) cudaFree(c->st_xy);
+    if (c->rc_xy) { cudaFree(c->rc_xy); cudaFree(c->rc_rate); cudaFree(c->rc_du); cudaFree(c->rc_surf); }
+    if (c->rc_pending) cudaFree(c->rc_pending);
     if (c->h_mail) cudaFreeHost(c->h_mail);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -810,6 +928,16 @@ int kmc_state_set(KmcCtx* c, const double* xy, int64_t n, int mem) {
     if (n > 0)
         CK(cudaMemcpyAsync(c->st_xy, xy, sizeof(double) * 2 * (size_t)n, mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     c->st_n = n;
+    c->rc_valid = false;            // an uploaded state has no history: the next rate table is a full sweep
+    if (mem == KMC_HOST) CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int kmc_state_move(KmcCtx* c, const double* xy, int64_t n, int mem) {
+    if (!c || (n > 0 && !xy)) return fail(KMC_E_ARG, "NULL argument");
+    if (n != c->st_n) return fail(KMC_E_ARG, "kmc_state_move: %lld positions for a state of %lld atoms (same atoms, new positions)", (long long)n, (long long)c->st_n);
+    if (n > 0)
+        CK(cudaMemcpyAsync(c->st_xy, xy, sizeof(double) * 2 * (size_t)n, mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     if (mem == KMC_HOST) CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1141,6 +1269,31 @@ int kmc_set_select_mode(KmcCtx* c, int mode) {
     return 0;
 }
 
+int kmc_set_rate_mode(KmcCtx* c, int mode, double threshold) {
+    if (!c || mode < 0 || mode > 1 || !(threshold >= 0.0)) return fail(KMC_E_ARG, "rate mode must be 0 (full sweep) or 1 (incremental), threshold >= 0");
+    c->rate_mode = mode;
+    c->rate_threshold = threshold;
+    c->rc_valid = false;
+    return 0;
+}
+
+int kmc_rates_update(KmcCtx* c, const KmcBins* sb, double threshold, double* rate, uint8_t* surf, double* du, int64_t* recomputed, int mem) {
+    if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
+    if (!(threshold >= 0.0)) return fail(KMC_E_ARG, "threshold must be >= 0");
+    int64_t redone = 0;
+    TRY(rates_update_impl(c, sb, threshold, &redone));
+    if (recomputed) *recomputed = redone;
+    const size_t n = (size_t)c->st_n;
+    const cudaMemcpyKind kind = mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (n) {
+        if (rate) CK(cudaMemcpyAsync(rate, c->rc_rate, sizeof(double) * n, kind, c->stream));
+        if (surf) CK(cudaMemcpyAsync(surf, c->rc_surf, n, kind, c->stream));
+        if (du) CK(cudaMemcpyAsync(du, c->rc_du, sizeof(double) * n, kind, c->stream));
+    }
+    if (mem == KMC_HOST) CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int kmc_deposit_place(KmcCtx* c, const KmcBins* sb, double u) {
     if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
     const int n = (int)c->st_n;
@@ -1186,6 +1339,7 @@ int kmc_deposit_place(KmcCtx* c, const KmcBins* sb, double u) {
                 CK(cudaMemcpyAsync(c->st_xy + 2 * (size_t)n, pos, sizeof(pos), cudaMemcpyHostToDevice, c->stream));   // :93
                 CK(cudaStreamSynchronize(c->stream));
                 c->st_n = n + 1;
+                TRY(rc_on_append(c));
                 return 0;
             }
         }
@@ -1236,15 +1390,19 @@ __global__ void k_remove_atom(const double2* __restrict__ in, int n, int k, doub
     if (i < n - 1) out[i] = in[i < k ? i : i + 1];
 }
 
-static int hop_place_impl(KmcCtx* c, const KmcBins* sb, int64_t k, double u, bool have_surface) {
+static int hop_place_impl(KmcCtx* c, const KmcBins* sb, int64_t k, double u, const uint8_t* surface_flags) {
     const int n = (int)c->st_n;
     if (k < 0 || k >= n) return fail(KMC_E_ARG, "hop index %lld out of range (n=%d)", (long long)k, n);
-    uint8_t* surf;
+    uint8_t* own;
     double* tmp;
-    TRY(slot(c, S_OUT1, (size_t)n, &surf));
+    TRY(slot(c, S_OUT1, (size_t)n, &own));
     TRY(slot(c, S_TMP0, 8, &tmp));
     // :239 SurfaceAtoms of the current state; kmc_event has just computed the same flags for the rate table
-    if (!have_surface) TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, nullptr, surf, nullptr, nullptr, nullptr, nullptr, nullptr));
+    const uint8_t* surf = surface_flags;
+    if (!surf) {
+        TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, nullptr, own, nullptr, nullptr, nullptr, nullptr, nullptr));
+        surf = own;
+    }
     LAUNCH(c, "hop_target", k_hop_target, 1, 1024, c->dp, (const double2*)c->st_xy, surf, n, (int)k, u, tmp);          // :240-248
     CK(cudaGetLastError());
     TRY(mail(c, tmp, 3 * sizeof(double)));
@@ -1254,6 +1412,7 @@ static int hop_place_impl(KmcCtx* c, const KmcBins* sb, int64_t k, double u, boo
     double* rest;
     TRY(slot(c, S_XN, (size_t)2 * n, &rest));
     LAUNCH(c, "misc_remove", k_remove_atom, cdiv(n, 256), 256, (const double2*)c->st_xy, n, (int)k, (double2*)rest);   // :241
+    TRY(rc_on_remove(c, (int)k));
     double hp[12];
     for (int i = 0; i < 6; ++i) {                                                 // :249-251
         const double t = i * M_PI / 3;
@@ -1286,12 +1445,13 @@ static int hop_place_impl(KmcCtx* c, const KmcBins* sb, int64_t k, double u, boo
     CK(cudaMemcpyAsync(c->st_xy, rest, sizeof(double) * 2 * (size_t)(n - 1), cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaMemcpyAsync(c->st_xy + 2 * (size_t)(n - 1), pos, sizeof(pos), cudaMemcpyHostToDevice, c->stream));   // :255
     CK(cudaStreamSynchronize(c->stream));
+    TRY(rc_on_append(c));
     return 0;
 }
 
 int kmc_hop_place(KmcCtx* c, const KmcBins* sb, int64_t k, double u) {
     if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
-    return hop_place_impl(c, sb, k, u, false);
+    return hop_place_impl(c, sb, k, u, nullptr);
 }
 
 int kmc_event(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_t max_ls, int32_t* kind_out, int64_t* hop_k_out, double* rtot_out,
@@ -1305,7 +1465,13 @@ int kmc_event(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_t max_ls
     TRY(slot(c, S_OUT1, (size_t)n, &surf));
     TRY(slot(c, S_OUT2, 2, &res));
     TRY(slot(c, S_OUT3, 1, &rt));
-    TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, rate, surf, nullptr, nullptr, nullptr, nullptr, nullptr));   // :318
+    if (c->rate_mode == 1) {        // incremental table: only the neighbourhoods that changed since the last event are redone
+        int64_t redone = 0;
+        TRY(rates_update_impl(c, sb, c->rate_threshold, &redone));
+        rate = c->rc_rate; surf = c->rc_surf;
+    } else {
+        TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, rate, surf, nullptr, nullptr, nullptr, nullptr, nullptr));   // :318
+    }
     LAUNCH(c, "select", k_select, 1, 32, c->dp, rate, surf, n, u0, res, rt, (double*)nullptr);                     // :319-324
     CK(cudaGetLastError());
     long long hres[2];
@@ -1318,7 +1484,7 @@ int kmc_event(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_t max_ls
         const int64_t who = c->hp.hop_index_mode == 0 ? hres[0] : hres[1];       // :327
         if (kind_out) *kind_out = 1;
         if (hop_k_out) *hop_k_out = who;
-        TRY(hop_place_impl(c, sb, who, u1, true));      // S_OUT1 still holds the surface flags of this state
+        TRY(hop_place_impl(c, sb, who, u1, surf));      // the surface flags of this state, just computed
     } else {
         if (kind_out) *kind_out = 0;
         if (hop_k_out) *hop_k_out = -1;

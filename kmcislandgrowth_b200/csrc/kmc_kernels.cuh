@@ -311,15 +311,28 @@ __global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellView ad, C
                                                      double* __restrict__ rate, uint8_t* __restrict__ is_surface,
                                                      double* __restrict__ delta_u, double* __restrict__ u_appx_o,
                                                      double* __restrict__ u_loc_o, int* __restrict__ n_a_o,
-                                                     int* __restrict__ n_s_o) {
+                                                     int* __restrict__ n_s_o,
+                                                     // incremental update (kmc_rates_update): only atoms that moved or whose
+                                                     // cell is marked are recomputed; their reference positions are refreshed
+                                                     const uint8_t* __restrict__ dirty_cell = nullptr, const uint8_t* __restrict__ self_dirty = nullptr,
+                                                     double2* __restrict__ ref_xy = nullptr, unsigned long long* __restrict__ recomputed = nullptr) {
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x & (G - 1);
-    const bool live = gid < n;
+    bool live = gid < n;
     double ua = 0, us = 0, la = 0, ls = 0;
     int ka = 0, ks = 0, idx = 0;
+    double2 pi = make_double2(0.0, 0.0);
     if (live) {
-        const double2 pi = ad.sxy[gid];
+        pi = ad.sxy[gid];
         idx = ad.sidx[gid];
+        if (dirty_cell) {
+            int nx, ny;
+            bin_index(P, pi.x, pi.y, nx, ny);
+            const int cell = flat_cell(P, nx, ny);
+            live = self_dirty[idx] || cell == P.ncell || dirty_cell[cell];     // atoms outside the grid are always redone
+        }
+    }
+    if (live) {
         const Stencil st = make_stencil(P, pi.x, pi.y);
         if (P.aa_mode == 0)
             for (int s = lane; s < n; s += G) ua += pair_energy(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2);
@@ -353,7 +366,56 @@ __global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellView ad, C
         if (u_loc_o) u_loc_o[idx] = loc;
         if (n_a_o) n_a_o[idx] = ka;
         if (n_s_o) n_s_o[idx] = ks;
+        if (ref_xy) ref_xy[idx] = pi;
+        if (recomputed) atomicAdd(recomputed, 1ull);
     }
+}
+
+// ---- incremental rate table: which cells hold atoms whose rate may have changed ----------------------
+// An atom's barrier depends on the atoms of its own 3x3(+seam) stencil (Bins.py:44-84, bins3x3 adatom sums), and the
+// relation "cell D is in the stencil of cell C" is symmetric (both wraps and the seam column come in pairs), so an atom
+// that moved by more than the threshold since its neighbours' rates were last computed dirties the stencil cells of its
+// old and of its new position.  `pending` = positions of atoms that were removed (HopAtom, 2DGrowth.py:241).
+__global__ void __launch_bounds__(256) k_rates_mark(DevParams P, const double2* __restrict__ xy, const double2* __restrict__ ref, int n, double thr2,
+                                                    const double2* __restrict__ pending, int npending, uint8_t* __restrict__ dirty_cell,
+                                                    uint8_t* __restrict__ self_dirty) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    auto mark = [&](double x, double y) {
+        const Stencil st = make_stencil(P, x, y);
+        for (int a = 0; a < st.nxs; ++a) {
+            const int cx = st.xs[a];
+            if (cx < 0 || cx >= P.nbx) continue;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const int cy = st.ys[b];
+                if (cy < 0 || cy >= P.nby) continue;
+                dirty_cell[cx * P.nby + cy] = 1;
+            }
+        }
+    };
+    if (i < n) {
+        const double2 p = xy[i], q = ref[i];
+        bool moved;
+        if (isnan(q.x)) moved = true;                                   // no cached entry (new atom)
+        else if (thr2 == 0.0) moved = (p.x != q.x) || (p.y != q.y);     // exact mode: any change at all
+        else {
+            const double dx = p.x - q.x, dy = p.y - q.y;
+            moved = dx * dx + dy * dy > thr2;
+        }
+        self_dirty[i] = moved ? 1 : 0;
+        if (moved) {
+            mark(p.x, p.y);
+            if (!isnan(q.x)) mark(q.x, q.y);
+        }
+    }
+    if (i < npending) mark(pending[i].x, pending[i].y);
+}
+
+// erase element k of an array (the cached tables follow HopAtom's np.delete, 2DGrowth.py:241)
+template <class T>
+__global__ void __launch_bounds__(256) k_erase_at(const T* __restrict__ src, int n, int k, T* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) dst[i] = src[i < k ? i : i + 1];
 }
 
 // Energy.py:170-172 / :77-95 and the closeness test of 2DGrowth.py:82-90.  One warp per probe point.

@@ -310,6 +310,11 @@ class Context(object):
         n = _count(k) // 2 if k is not None else 0
         check(self.lib.kmc_state_set(self.handle, p, n, mem if mem is not None else KMC_HOST))
 
+    def state_move(self, xy):
+        """new positions for the same atoms; keeps the incremental rate table's history (kmc_state_move)"""
+        k, p, mem = _in(xy)
+        check(self.lib.kmc_state_move(self.handle, p, _count(k) // 2, mem if mem is not None else KMC_HOST))
+
     def state_get(self):
         n = int(self.lib.kmc_state_count(self.handle))
         out = np.empty(2 * n)
@@ -326,6 +331,21 @@ class Context(object):
         if rc != 0 and rc != _lib.KMC_E_ITERCAP:
             check(rc)
         return st
+
+    def set_rate_mode(self, mode, threshold=0.0):
+        """0: every event rebuilds the whole rate table (the reference, 2DGrowth.py:318); 1: kmc_event keeps an incremental
+        table and recomputes only neighbourhoods in which an atom moved by more than `threshold` Angstrom (0 = exact)"""
+        check(self.lib.kmc_set_rate_mode(self.handle, int(mode), float(threshold)))
+
+    def rates_update(self, sbins, threshold=0.0):
+        """incremental rate table of the resident state -> dict(rate, is_surface, delta_u, recomputed)"""
+        n = self.state_count()
+        r = dict(rate=np.zeros(n), is_surface=np.zeros(n, np.uint8), delta_u=np.zeros(n))
+        redone = C.c_int64(0)
+        check(self.lib.kmc_rates_update(self.handle, sbins.handle, float(threshold), _ptr(r["rate"]), _ptr(r["is_surface"]),
+                                        _ptr(r["delta_u"]), C.byref(redone), _lib.KMC_HOST))
+        r["recomputed"] = int(redone.value)
+        return r
 
     def set_select_mode(self, mode):
         check(self.lib.kmc_set_select_mode(self.handle, int(mode)))

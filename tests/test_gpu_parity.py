@@ -406,6 +406,86 @@ def test_line_polynomial_and_per_candidate_paths_against_oracle():
     assert np.max(np.abs(x - xo)) < 1e-7
 
 
+def test_incremental_rate_table_exact_mode_follows_events():
+    """kmc_rates_update with threshold 0 must equal the full sweep bit for bit, event after event, through the index
+    shifts of HopAtom (np.delete + append, 2DGrowth.py:241,255) and DepositAdatom (:93); and an event loop that uses the
+    incremental table (kmc_set_rate_mode 1, threshold 0) follows the same trajectory as the full-sweep loop."""
+    from kmcislandgrowth_b200 import Growth, runtime, workloads
+    gv = workloads.constants_for(48, 12, 12, aa_mode=1, hop_index_mode=1, deposit_mode=1)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, 500, seed=21, sigma=0.02)
+    rng = np.random.default_rng(5)
+    us = rng.uniform(0, 1, (10, 2))
+    sims = [Growth.Simulation(adatoms=ad, substrate=sub, params=runtime.params_from(gv)) for _ in range(2)]
+    sims[1].ctx.set_rate_mode(1, 0.0)
+    kinds = []
+    try:
+        for s in sims:
+            s.ctx.relax(s.sbins, 16, 1e-4, 100)
+        first = sims[1].ctx.rates_update(sims[1].sbins, 0.0)
+        assert first["recomputed"] == sims[1].ctx.state_count()          # no history yet: full sweep
+        again = sims[1].ctx.rates_update(sims[1].sbins, 0.0)
+        assert again["recomputed"] == 0                                   # nothing moved: nothing redone
+        for t in range(10):
+            r0 = sims[0].step(us[t, 0], us[t, 1], 40)
+            r1 = sims[1].step(us[t, 0], us[t, 1], 40)
+            kinds.append(r0["kind"])
+            assert (r0["kind"], r0["line_searches"]) == (r1["kind"], r1["line_searches"])
+            assert np.array_equal(sims[0].adatoms, sims[1].adatoms)
+            full = sims[0].ctx.rates(sims[0].adatoms, sims[0].sbins)
+            inc = sims[1].ctx.rates_update(sims[1].sbins, 0.0)
+            assert np.array_equal(inc["rate"], full["rate"]) and np.array_equal(inc["is_surface"], full["is_surface"])
+            assert np.array_equal(inc["delta_u"], full["delta_u"])
+        assert 1 in kinds
+        # a deposition (hop rates dwarf the deposition rate here, so it is placed explicitly): appended atom, no history
+        for s_ in sims:
+            s_.ctx.deposit_place(s_.sbins, 0.3)
+            s_.ctx.relax(s_.sbins, 16, 1e-4, 40)
+        full = sims[0].ctx.rates(sims[0].adatoms, sims[0].sbins)
+        inc = sims[1].ctx.rates_update(sims[1].sbins, 0.0)
+        assert inc["rate"].size == full["rate"].size == 501
+        assert np.array_equal(inc["rate"], full["rate"]) and np.array_equal(inc["is_surface"], full["is_surface"])
+    finally:
+        for s in sims:
+            s.close()
+
+
+def test_incremental_rate_table_touches_only_the_neighbourhood():
+    """Moving ONE atom dirties only the cells of its old and new 3x3 stencils: a small fraction of the film is recomputed,
+    and the table still equals the full sweep exactly (threshold 0).  With a threshold, sub-threshold jitter of every atom
+    recomputes nothing and leaves rates within the corresponding tolerance."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(128, 16, 16, aa_mode=1)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, 1500, seed=8, sigma=0.02)       # 12 layers: every atom inside the bin grid
+    ctx = runtime.Context(runtime.params_from(gv), 0)
+    sb = ctx.bins_create(sub)
+    try:
+        ctx.state_set(ad)
+        assert ctx.rates_update(sb, 0.0)["recomputed"] == 1500
+        x = ad.copy()
+        top = int(np.argmax(x[1::2]))
+        x[2 * top] += 0.37
+        x[2 * top + 1] += 0.21
+        # kmc_state_move: same atoms, new positions (kmc_state_set would drop the table's history)
+        ctx.state_move(x)
+        inc = ctx.rates_update(sb, 0.0)
+        full = ctx.rates(x, sb)
+        assert 0 < inc["recomputed"] < 250, inc["recomputed"]            # ~ the atoms of 2 x 9 cells, not 1500
+        assert np.array_equal(inc["rate"], full["rate"]) and np.array_equal(inc["is_surface"], full["is_surface"])
+        # sub-threshold jitter everywhere: nothing is redone, rates stay within beta * |dU/dr| * jitter
+        rng = np.random.default_rng(3)
+        y = x + rng.normal(0, 2e-5, x.shape)
+        ctx.state_move(y)
+        inc2 = ctx.rates_update(sb, 1e-3)
+        assert inc2["recomputed"] == 0
+        full2 = ctx.rates(y, sb)
+        m = full2["is_surface"].astype(bool)
+        assert np.array_equal(inc2["is_surface"].astype(bool), m)
+        assert np.max(np.abs(inc2["rate"][m] - full2["rate"][m]) / full2["rate"][m]) < 5e-2
+    finally:
+        sb.close()
+        ctx.close()
+
+
 def test_checkpoint_and_island_statistics(tmp_path):
     """Simulation.save / load round trip, the KMC clock extension, and island statistics of a GPU trajectory equal to
     those of the reference's trajectory (same uniforms -> same states -> same observables)."""
