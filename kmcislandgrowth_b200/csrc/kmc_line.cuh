@@ -112,34 +112,59 @@ __device__ __forceinline__ void pair_line_part(const DevParams& P, double dx0, d
 constexpr int PD = 6;
 constexpr double POLY_UMAX = 3e-3;
 
-// returns false when the pair was not expanded (invalid lane, or it must take the per-candidate path); inv0 = 1/r0^2
-__device__ __forceinline__ bool pair_line_poly(const DevParams& P, bool valid, double dx0, double dy0, double ddx, double ddy, double E,
-                                               double inv0, double (&acc)[PD + 1]) {
+constexpr double POLY_UMAX3 = 5e-5;    // below this a degree-3 polynomial is exact to rounding (first dropped term 126 u^4 < 1e-15)
+
+// per-pair quantities of the expansion; ok == false: the pair is not expanded (invalid lane, or it must take the
+// per-candidate path) and every coefficient below is zero, so accumulating it is harmless (branch-free: the chains of the
+// two pairs a lane holds interleave, no basic-block boundary between them)
+struct PolyPrep {
+    double b, c, Q3, Q6;
+    bool ok, small;
+};
+__device__ __forceinline__ PolyPrep pair_line_prep(const DevParams& P, bool valid, double dx0, double dy0, double ddx, double ddy, double E, double inv0) {
     constexpr double tm = 0.5 * (KC - 1);
+    PolyPrep r;
     const double mx = fma(tm, ddx, dx0), my = fma(tm, ddy, dy0);      // displacement at the middle of the line
     const double A = fma(mx, mx, my * my);
     const double Bh = fma(mx, ddx, my * ddy);                         // B/2
     const double C = fma(ddx, ddx, ddy * ddy);
     const bool no_wrap = fabs(dx0) + (KC - 1) * fabs(ddx) < P.halfL - 1e-9;
-    const bool quiet = fma(C, tm * tm, 2.0 * tm * fabs(Bh)) < POLY_UMAX * A;      // strict: A == 0 is never quiet
-    // branch-free: a pair that is not expanded runs the same instructions on harmless operands and adds zeros, so that
-    // the chains of two pairs held by one lane interleave (no basic-block boundary between them)
-    const bool ok = valid && no_wrap && quiet;
-    const double q = fast_rcp(ok ? A * inv0 : 1.0);          // r0^2 / A
-    const double w = q * inv0;                    // 1 / A
-    const double b = ok ? (Bh + Bh) * w : 0.0, c = ok ? C * w : 0.0;
+    const double umax_A = fma(C, tm * tm, 2.0 * tm * fabs(Bh));       // max |u| * A over the line
+    const bool quiet = umax_A < POLY_UMAX * A;                        // strict: A == 0 is never quiet
+    r.ok = valid && no_wrap && quiet;
+    r.small = umax_A < POLY_UMAX3 * A;
+    const double q = fast_rcp(r.ok ? A * inv0 : 1.0);        // r0^2 / A
+    const double w = q * inv0;                               // 1 / A
+    r.b = r.ok ? (Bh + Bh) * w : 0.0;
+    r.c = r.ok ? C * w : 0.0;
     const double q3 = q * q * q;
-    const double Q3 = ok ? E * q3 : 0.0, Q6 = Q3 * q3;
-    // e(u) = sum_k g_k u^k,  g_k = (-1)^k (C(k+5,5) Q6 - 2 C(k+2,2) Q3)
+    r.Q3 = r.ok ? E * q3 : 0.0;
+    r.Q6 = r.Q3 * q3;
+    return r;
+}
+
+// e(u) = sum_k g_k u^k,  g_k = (-1)^k (C(k+5,5) Q6 - 2 C(k+2,2) Q3); composition G(u(t)) by Horner in u, every
+// intermediate truncated to the degree that can still reach t^DEG: P_k = g_k + u P_{k+1}, (u p)[m] = b p[m-1] + c p[m-2]
+template <int DEG>
+__device__ __forceinline__ void pair_line_acc(const PolyPrep& r, double (&acc)[PD + 1]) {
+    const double b = r.b, c = r.c, Q3 = r.Q3, Q6 = r.Q6;
     const double g0 = fma(1.0, Q6, -2.0 * Q3);
     const double g1 = fma(-6.0, Q6, 6.0 * Q3);
     const double g2 = fma(21.0, Q6, -12.0 * Q3);
     const double g3 = fma(-56.0, Q6, 20.0 * Q3);
+    if (DEG == 3) {
+        double p0 = g3, p1, p2;
+        p1 = b * p0;                                  p0 = g2;       // P2: degree 1
+        p2 = fma(b, p1, c * p0); p1 = b * p0;         p0 = g1;       // P1: degree 2
+        acc[3] = fma(b, p2, fma(c, p1, acc[3]));
+        acc[2] = fma(b, p1, fma(c, p0, acc[2]));
+        acc[1] = fma(b, p0, acc[1]);
+        acc[0] += g0;
+        return;
+    }
     const double g4 = fma(126.0, Q6, -30.0 * Q3);
     const double g5 = fma(-252.0, Q6, 42.0 * Q3);
     const double g6 = fma(462.0, Q6, -56.0 * Q3);
-    // composition G(u(t)) by Horner in u, every intermediate truncated to the degree that can still reach t^PD:
-    // P_k = g_k + u P_{k+1}, deg P_k = PD - k;  (u p)[m] = b p[m-1] + c p[m-2]
     double p0 = g6, p1, p2, p3, p4, p5;
     p1 = b * p0;                                                  p0 = g5;       // P5: degree 1
     p2 = fma(b, p1, c * p0); p1 = b * p0;                         p0 = g4;       // P4: degree 2
@@ -154,7 +179,16 @@ __device__ __forceinline__ bool pair_line_poly(const DevParams& P, bool valid, d
     acc[2] = fma(b, p1, fma(c, p0, acc[2]));
     acc[1] = fma(b, p0, acc[1]);
     acc[0] += g0;
-    return ok;
+}
+
+// one pair; returns false when it was not expanded.  The degree is chosen per WARP: when every expanded pair of the round
+// moves by |u| < POLY_UMAX3 (the usual case in the long tail of a relaxation) three powers of u are exact to rounding.
+__device__ __forceinline__ bool pair_line_poly(const DevParams& P, bool valid, double dx0, double dy0, double ddx, double ddy, double E,
+                                               double inv0, double (&acc)[PD + 1]) {
+    const PolyPrep r = pair_line_prep(P, valid, dx0, dy0, ddx, ddy, E, inv0);
+    if (__all_sync(0xffffffffu, !r.ok || r.small)) pair_line_acc<3>(r, acc);
+    else pair_line_acc<PD>(r, acc);
+    return r.ok;
 }
 
 // one candidate of one pair, general form (min-image wrap per candidate, r == 0 excluded: Periodic.py:8-20, Energy.py:28)

@@ -453,10 +453,17 @@ __device__ __forceinline__ void relax2_round_compute2(const Relax2Args& R, const
     const DevParams& P = R.P;
     const PairGeo ga = relax2_round_geo(P, LA, inv_step), gb = relax2_round_geo(P, LB, inv_step);
     if (R.debug == 1) { if (ga.valid) acc[0] += ga.dx0 + ga.dy0 + ga.ddx + ga.ddy; if (gb.valid) acc[0] += gb.dx0 + gb.dy0 + gb.ddx + gb.ddy; return; }
-    const bool oka = pair_line_poly(P, ga.valid, ga.dx0, ga.dy0, ga.ddx, ga.ddy, ga.is_sub ? P.E_as : P.E_a, ga.is_sub ? P.inv_ras2 : P.inv_ra2, acc);
-    const bool okb = pair_line_poly(P, gb.valid, gb.dx0, gb.dy0, gb.ddx, gb.ddy, gb.is_sub ? P.E_as : P.E_a, gb.is_sub ? P.inv_ras2 : P.inv_ra2, acc);
-    relax2_slow_pairs(P, ga.valid && !oka, ga.dx0, ga.dy0, ga.ddx, ga.ddy, ga.is_sub, lane, eslow);
-    relax2_slow_pairs(P, gb.valid && !okb, gb.dx0, gb.dy0, gb.ddx, gb.ddy, gb.is_sub, lane, eslow);
+    const PolyPrep ra = pair_line_prep(P, ga.valid, ga.dx0, ga.dy0, ga.ddx, ga.ddy, ga.is_sub ? P.E_as : P.E_a, ga.is_sub ? P.inv_ras2 : P.inv_ra2);
+    const PolyPrep rb = pair_line_prep(P, gb.valid, gb.dx0, gb.dy0, gb.ddx, gb.ddy, gb.is_sub ? P.E_as : P.E_a, gb.is_sub ? P.inv_ras2 : P.inv_ra2);
+    if (__all_sync(0xffffffffu, (!ra.ok || ra.small) && (!rb.ok || rb.small))) {       // warp-uniform choice of the degree
+        pair_line_acc<3>(ra, acc);
+        pair_line_acc<3>(rb, acc);
+    } else {
+        pair_line_acc<PD>(ra, acc);
+        pair_line_acc<PD>(rb, acc);
+    }
+    relax2_slow_pairs(P, ga.valid && !ra.ok, ga.dx0, ga.dy0, ga.ddx, ga.ddy, ga.is_sub, lane, eslow);
+    relax2_slow_pairs(P, gb.valid && !rb.ok, gb.dx0, gb.dy0, gb.ddx, gb.ddy, gb.is_sub, lane, eslow);
 }
 
 // all items k = w0, w0 + nw, ... of this warp; `wit` = the warp's cached copies of the first R2_WI of them
