@@ -21,8 +21,28 @@ constexpr int LT_TILE = 256;  // neighbour atoms staged per pass
 constexpr int LT_THREADS = 128;
 
 // candidate a of coordinate v moving along s: v + ((a*s)/20)/scale, the reference's operation order
+// Both quotients are formed without the division subroutine and are still the correctly rounded IEEE results:
+//  x/20: q0 = RN(x*y) with y = RN(1/20), r = x - 20 q0 (exact in an FMA), q = RN(q0 + r*y) -- Markstein's correction, which
+//        yields the correctly rounded quotient when y is the correctly rounded reciprocal (20 = 1.25*2^4: no exceptional
+//        mantissa) and no intermediate is subnormal; operands outside [1e-280, 1e280] take the real division;
+//  q/scale: every scale the relaxation uses is a power of two (16 * 2^k), for which multiplying by the exact reciprocal IS the
+//        quotient; any other scale takes the real division.
 __device__ __forceinline__ double cand1(double v, double s, int a, double scale) {
-    return __dadd_rn(v, __ddiv_rn(__ddiv_rn(__dmul_rn((double)a, s), 20.0), scale));
+    const double x = __dmul_rn((double)a, s);
+    double q;
+    const double ax = fabs(x);
+    if (ax < 1e280 && (ax > 1e-280 || ax == 0.0)) {
+        const double y = 0.05;
+        const double q0 = __dmul_rn(x, y);
+        const double r = __fma_rn(-20.0, q0, x);
+        q = __fma_rn(r, y, q0);
+    } else {
+        q = __ddiv_rn(x, 20.0);
+    }
+    const long long sb = __double_as_longlong(scale);
+    const bool pow2 = (sb & 0x000fffffffffffffLL) == 0 && scale > 1e-300 && scale < 1e300;
+    const double t = pow2 ? __dmul_rn(q, __ddiv_rn(1.0, scale)) : __ddiv_rn(q, scale);
+    return __dadd_rn(v, t);
 }
 __device__ __forceinline__ double2 cand2(double2 p, double2 s, int a, double scale) {
     return make_double2(cand1(p.x, s.x, a, scale), cand1(p.y, s.y, a, scale));
