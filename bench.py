@@ -354,9 +354,9 @@ def run_ours(args):
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum of k_relax2 from the committed ncu --set full capture
-                         # (profiles/r1m_relax2_ncu.md: 1.635 MB for a 200-line-search launch), scaled to this run's
+                         # (profiles/r1m_relax2_ncu.md, revision p: 1.017 MB for a 200-line-search launch), scaled to this run's
                          # line searches per launch: the working set is L2 resident, DRAM sees first touches only
-                         "traffic": 1634816.0 / 200.0 * ls_mean, "traffic_source": "profiles/r1m_relax2_ncu.md (8.2 kB per line search)",
+                         "traffic": 1016832.0 / 200.0 * ls_mean, "traffic_source": "profiles/r1m_relax2_ncu.md, revision p (5.1 kB per line search)",
                          "algorithmic_bytes_per_launch": abytes, "bytes_detail": binfo,
                          "avg_launch_us": k_ms * 1e3, "launches": ek["launches"],
                          "kernel_share_of_gpu_time": ek["ms"] / total_kernel_ms if total_kernel_ms else None,

@@ -26,6 +26,10 @@ namespace kmc {
 #endif
 constexpr int R2_THREADS = KMC_R2_THREADS;
 constexpr int R2_NE = KC + PD + 1;  // values reduced per line search: KC per-candidate sums (pairs that are not expanded) + the polynomial
+#ifndef KMC_R2_FB
+#define KMC_R2_FB 8
+#endif
+constexpr int R2_FB = KMC_R2_FB;       // neighbours fetched and evaluated per batch and lane in the force sweep
 #ifndef KMC_R2_CHUNK
 #define KMC_R2_CHUNK 64
 #endif
@@ -639,11 +643,11 @@ __device__ __forceinline__ void flat_forces(const DevParams& P, const double2* p
                                             double E, double r0sq, double& fx, double& fy, unsigned long long& visits) {
     const int c0 = e.x - b.x, c1 = c0 + (e.y - b.y), c2 = c1 + (e.z - b.z), tot = c2 + (e.w - b.w);
     const double E12 = 12.0 * E;
-    for (int t = lane; t < tot; t += 8 * G) {
-        double2 p[8];
+    for (int t = lane; t < tot; t += R2_FB * G) {
+        double2 p[R2_FB];
         bool far = false;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < R2_FB; ++k) {
             const int tk = min(t + k * G, tot - 1);
             const int sl = tk < c0 ? b.x + tk : (tk < c1 ? b.y + (tk - c0) : (tk < c2 ? b.z + (tk - c1) : b.w + (tk - c2)));
             p[k] = ptr[sl];
@@ -651,13 +655,13 @@ __device__ __forceinline__ void flat_forces(const DevParams& P, const double2* p
         }
         if (far || P.precision == 1) {      // |dx| >= L (atoms that drifted by a box length) or fp32 pair terms: the general form
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < R2_FB; ++k)
                 if (t + k * G < tot) { acc_force(P, xi, yi, p[k], E, r0sq, fx, fy); ++visits; }
         } else {
             // branch-free: the eight pair chains are independent and interleave (one basic block); a slot past the end
             // holds a clamped duplicate and contributes a zero coefficient.  Same arithmetic as acc_force.
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < R2_FB; ++k) {
                 double dx = p[k].x - xi;
                 dx = (dx < 0.0) ? __dadd_rn(dx, P.L) : dx;
                 dx = (dx > P.halfL) ? __dadd_rn(dx, -P.L) : dx;
