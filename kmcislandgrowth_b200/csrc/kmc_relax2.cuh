@@ -27,9 +27,10 @@ namespace kmc {
 constexpr int R2_THREADS = KMC_R2_THREADS;
 constexpr int R2_NE = KC + PD + 1;  // values reduced per line search: KC per-candidate sums (pairs that are not expanded) + the polynomial
 #ifndef KMC_R2_FB
-#define KMC_R2_FB 8
+#define KMC_R2_FB 4
 #endif
-constexpr int R2_FB = KMC_R2_FB;       // neighbours fetched and evaluated per batch and lane in the force sweep
+constexpr int R2_FB = KMC_R2_FB;       // neighbours fetched and evaluated per batch and lane in the force sweep (measured G phase,
+                                       // us per line search: 8 -> 8.5, 7 -> 8.4, 6 -> 8.2, 5 -> 8.2, 4 -> 8.0)
 #ifndef KMC_R2_CHUNK
 #define KMC_R2_CHUNK 64
 #endif
