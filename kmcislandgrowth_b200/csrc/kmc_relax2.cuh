@@ -26,6 +26,9 @@ namespace kmc {
 #endif
 constexpr int R2_THREADS = KMC_R2_THREADS;
 constexpr int R2_NE = KC + PD + 1;  // values reduced per line search: KC per-candidate sums (pairs that are not expanded) + the polynomial
+#ifndef KMC_R2_ETMA
+#define KMC_R2_ETMA 1      // 1: energy-phase operands by TMA bulk copies (cp.async.bulk + mbarrier); 0: plain loads (same time: 7.2 us E phase either way)
+#endif
 #ifndef KMC_R2_FB
 #define KMC_R2_FB 4
 #endif
@@ -919,12 +922,41 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     unsigned long long t_mark = gtimer();
 
     // request the operands of an energy phase: positions, directions and mover flags of slots [emin, emax)
-    auto issue_e = [&](const double2* p, const double2* d) {
+    [[maybe_unused]] auto issue_e = [&](const double2* p, const double2* d) {
         if (threadIdx.x == 0) {
             const unsigned int ne = (unsigned int)(er.emax - er.emin);
             bulk_load3(S.epos, p + er.emin, ne * 16u, S.edir, d + er.emin, ne * 16u, S.eflag, R.flag + er.emin, (ne + 15u) & ~15u, &S.mbar_e);
         }
         e_inflight = true;
+        e_fresh = true;
+    };
+    // the same operands with plain loads: two elements per thread and array, all requested before the first is stored (one L2
+    // round trip); `with_maxf` folds the max|F|^2 reduction of the control step into the same round trip.  The caller
+    // synchronises the block.  (Alternative to the bulk copies, KMC_R2_ETMA 0; measured equal.)
+    [[maybe_unused]] auto load_e = [&](const double2* p, const double2* d, bool with_maxf) {
+        const int ne = er.emax - er.emin;
+        double2 pv[R2_STAGE / R2_THREADS], dv[R2_STAGE / R2_THREADS];
+        uint4 fv = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < R2_STAGE / R2_THREADS; ++k) {
+            const int i = threadIdx.x + k * R2_THREADS;
+            pv[k] = i < ne ? p[er.emin + i] : make_double2(0.0, 0.0);
+            dv[k] = i < ne ? d[er.emin + i] : make_double2(0.0, 0.0);
+        }
+        const int nf16 = (ne + 15) >> 4;
+        if ((int)threadIdx.x < nf16) fv = *reinterpret_cast<const uint4*>(R.flag + er.emin + 16 * threadIdx.x);
+        if (with_maxf && threadIdx.x < 32) {
+            double mf = 0.0;
+            for (int b = lane; b < nblk; b += 32) mf = fmax(mf, R.red[(size_t)b * 4 + 3]);
+            for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+            if (lane == 0) S.ctl[3] = mf;
+        }
+#pragma unroll
+        for (int k = 0; k < R2_STAGE / R2_THREADS; ++k) {
+            const int i = threadIdx.x + k * R2_THREADS;
+            if (i < ne) { S.epos[i] = pv[k]; S.edir[i] = dv[k]; }
+        }
+        if ((int)threadIdx.x < nf16) *reinterpret_cast<uint4*>(S.eflag + 16 * threadIdx.x) = fv;
         e_fresh = true;
     };
     // candidate sums, argmin, x_np, partial reductions; returns after the barrier that publishes x_np
@@ -938,8 +970,13 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         // ---------------- E
         unsigned long long t_blk = (R.debug == 8 && threadIdx.x == 0) ? gtimer() : 0ull;
         if (er.emax > er.emin && !e_fresh) {            // first line of a pass: nothing was requested ahead
+#if KMC_R2_ETMA
             if (e_inflight) { mbar_wait(&S.mbar_e, e_parity); e_parity ^= 1u; }
             issue_e(pos, sdir);
+#else
+            load_e(pos, sdir, false);
+            __syncthreads();
+#endif
         }
         if (blockIdx.x == 0) {          // ordered list of mover slots
             const int T = blockDim.x, t = threadIdx.x;
@@ -982,9 +1019,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             EOperands O;
             O.pos = pos; O.dir = sdir; O.flag = R.flag; O.sub = R.sub.sxy;
             if (er.emax > er.emin) {
+#if KMC_R2_ETMA
                 mbar_wait(&S.mbar_e, e_parity);
                 e_parity ^= 1u;
                 e_inflight = false;
+#endif
                 e_fresh = false;
                 O.pos = S.epos - er.emin; O.dir = S.edir - er.emin; O.flag = S.eflag - er.emin;
             }
@@ -1169,8 +1208,14 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(6)
         // the next line search (if there is one) starts from x_np with the directions and flags just published: request
         // its operands now, the copies land while the control arithmetic runs
+#if KMC_R2_ETMA
         if (er.emax > er.emin) issue_e(R.pos[cur ^ 1], R.sdir[cs]);
-        if (threadIdx.x < 32) {
+        const bool maxf_done = false;
+#else
+        const bool maxf_done = er.emax > er.emin;
+        if (maxf_done) load_e(R.pos[cur ^ 1], R.sdir[cs], true);
+#endif
+        if (!maxf_done && threadIdx.x < 32) {
             double mf = 0.0;
             for (int b = lane; b < nblk; b += 32) mf = fmax(mf, R.red[(size_t)b * 4 + 3]);
             for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
