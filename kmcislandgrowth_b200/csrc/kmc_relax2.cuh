@@ -1,17 +1,22 @@
 // kmc_relax2.cuh -- Relaxation (2DGrowth.py:97-166) as one persistent cooperative kernel, second
 // generation: the trajectory lives in CELL-SORTED order for the whole relaxation (positions,
 // directions, original indices), so every pass is coalesced and free of gathers; the line-search
-// energy is split into equal-sized work items (<= 64 pairs) that are dealt to warps statically,
-// which balances the grid and keeps every sum in a fixed order (bit-reproducible runs); the CG
-// update and the mover flags of the next line are fused into the force phase, leaving three grid
-// barriers per line search:
+// energy is split into work items (<= 64 pairs) of which every block owns a contiguous range (its
+// operands are staged in shared memory by TMA bulk copies requested one phase ahead), every sum is
+// formed in a fixed order (bit-reproducible runs); the 20 candidate energies of a pair are ONE
+// Taylor polynomial (kmc_line.cuh: pair_line_poly) whose coefficients are summed over the pairs;
+// the CG update and the mover flags of the next line are fused into the force phase, leaving three
+// grid barriers per line search:
 //
-//   E: line-search energy over the work items (+ ordered mover list by block 0)            ||
-//      [F: mover fix-up, only when movers exist                                            ||]
-//   S: candidate sums, first argmin, x_np = candidate, top/bot/min-y partials, cell check   ||
+//   E: polynomial / per-candidate sums over the work items; block 0: ordered mover list and, for
+//      up to R2_FIX_INLINE movers, their per-candidate evaluation                             ||
+//      [F: mover fix-up phase, only for more movers                                           ||]
+//   S: sums over blocks, candidate energies, first argmin, x_np, top/bot/min-y partials, cell check ||
 //      [rebuild of the sorted state when a mover really changed cell at the winner]
-//   G: forces at x_np, max|F|^2 partials, s <- F + beta s, mover flags of the next line    ||
-//   C: control (every block, identical arithmetic): converged / stalled / out of bounds / continue
+//   G: forces at x_np (one pass, T/atoms lanes per atom), max|F|^2 partials, s <- F + beta s,
+//      mover flags of the next line                                                           ||
+//   C: control (every block, identical arithmetic): converged / stalled / out of bounds / continue;
+//      a restart from the original positions reuses the sorted layout and F(x0) when it can
 #pragma once
 #include "kmc_line.cuh"
 #include "kmc_relax.cuh"
@@ -767,9 +772,8 @@ __device__ __forceinline__ double group_sum_rt(double v, int G) {
     return v;
 }
 
-// Every block owns a contiguous chunk of slots (cell-sorted, so its atoms share stencils in L1).  The chunk is
-// processed in rounds; each round gives every atom G lanes, G = the largest power of two that lets the round
-// cover at least half of what is left (64 atoms x 8 lanes, then 4 atoms x 32 lanes for 68 atoms on 512 threads).
+// Every block owns a contiguous chunk of slots (cell-sorted, so its atoms share one neighbourhood, kept in shared memory).
+// The chunk is processed in ONE pass with T/atoms lanes per atom (see below); larger chunks take several passes.
 __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2* pos, double2* sdir, const int* oidx, int mode, double beta,
                                               double scale, bool count_pairs, Relax2Smem& S, unsigned int& parity, int smin, int smax,
                                               bool issue_here, unsigned long long* tm = nullptr) {

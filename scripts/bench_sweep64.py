@@ -17,6 +17,7 @@ nev = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 if world > 1:
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 torch.cuda.set_device(local)
 grid = replicas.sweep_grid()

@@ -486,6 +486,29 @@ def test_incremental_rate_table_touches_only_the_neighbourhood():
         ctx.close()
 
 
+@pytest.mark.parametrize("W,Hs,Ha,n,cap", [(512, 16, 48, 20000, 8), (1024, 16, 96, 80000, 3)])
+def test_relaxation_large_chunks_follow_the_oracle(W, Hs, Ha, n, cap):
+    """Films whose per-block chunk exceeds the shared-memory caches of k_relax2 (more than 80 atoms per block: stencil
+    ranges from global memory; more than 512: several passes per phase; neighbourhoods beyond the staging capacity:
+    global reads): the first line searches must follow the oracle exactly like the small cases do."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(W, Hs, Ha, aa_mode=1)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, n, seed=W + n, sigma=0.03)
+    o = _oracle_for(gv)
+    osb = o.PutInBins(sub)
+    xo, sto, rc = o.Relaxation(ad, osb, max_line_searches=cap)
+    ctx = runtime.Context(runtime.params_from(gv), 0)
+    sb = ctx.bins_create(sub)
+    try:
+        ctx.state_set(ad)
+        st = ctx.relax(sb, 16, 1e-4, cap)
+        assert (int(st.line_searches), int(st.restarts)) == (int(sto.line_searches), int(sto.restarts))
+        assert np.max(np.abs(ctx.state_get() - xo)) < 1e-8
+    finally:
+        sb.close()
+        ctx.close()
+
+
 def test_checkpoint_and_island_statistics(tmp_path):
     """Simulation.save / load round trip, the KMC clock extension, and island statistics of a GPU trajectory equal to
     those of the reference's trajectory (same uniforms -> same states -> same observables)."""
