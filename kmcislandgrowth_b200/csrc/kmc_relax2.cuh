@@ -31,9 +31,6 @@ namespace kmc {
 #endif
 constexpr int R2_THREADS = KMC_R2_THREADS;
 constexpr int R2_NE = KC + PD + 1;  // values reduced per line search: KC per-candidate sums (pairs that are not expanded) + the polynomial
-#ifndef KMC_R2_ETMA
-#define KMC_R2_ETMA 1      // 1: energy-phase operands by TMA bulk copies (cp.async.bulk + mbarrier); 0: plain loads (same time: 7.2 us E phase either way)
-#endif
 #ifndef KMC_R2_FB
 #define KMC_R2_FB 4
 #endif
@@ -904,6 +901,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     unsigned int e_parity = 0;
     bool e_inflight = false;         // copies of the energy-phase operands requested and not yet waited for
     bool e_fresh = false;            // ... and they are the operands of the NEXT energy phase
+    bool stall_check = false;        // the stall test applies from the second line search of a pass on
     bool layout_x0 = false;          // the sorted layout is the one built from x0 and sdir[cs ^ 1] holds F(x0)
     if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); mbar_init(&S.mbar_e, 1); }
     __syncthreads();
@@ -926,7 +924,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     unsigned long long t_mark = gtimer();
 
     // request the operands of an energy phase: positions, directions and mover flags of slots [emin, emax)
-    [[maybe_unused]] auto issue_e = [&](const double2* p, const double2* d) {
+    auto issue_e = [&](const double2* p, const double2* d) {
         if (threadIdx.x == 0) {
             const unsigned int ne = (unsigned int)(er.emax - er.emin);
             bulk_load3(S.epos, p + er.emin, ne * 16u, S.edir, d + er.emin, ne * 16u, S.eflag, R.flag + er.emin, (ne + 15u) & ~15u, &S.mbar_e);
@@ -934,37 +932,12 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         e_inflight = true;
         e_fresh = true;
     };
-    // the same operands with plain loads: two elements per thread and array, all requested before the first is stored (one L2
-    // round trip); `with_maxf` folds the max|F|^2 reduction of the control step into the same round trip.  The caller
-    // synchronises the block.  (Alternative to the bulk copies, KMC_R2_ETMA 0; measured equal.)
-    [[maybe_unused]] auto load_e = [&](const double2* p, const double2* d, bool with_maxf) {
-        const int ne = er.emax - er.emin;
-        double2 pv[R2_STAGE / R2_THREADS], dv[R2_STAGE / R2_THREADS];
-        uint4 fv = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int k = 0; k < R2_STAGE / R2_THREADS; ++k) {
-            const int i = threadIdx.x + k * R2_THREADS;
-            pv[k] = i < ne ? p[er.emin + i] : make_double2(0.0, 0.0);
-            dv[k] = i < ne ? d[er.emin + i] : make_double2(0.0, 0.0);
-        }
-        const int nf16 = (ne + 15) >> 4;
-        if ((int)threadIdx.x < nf16) fv = *reinterpret_cast<const uint4*>(R.flag + er.emin + 16 * threadIdx.x);
-        if (with_maxf && threadIdx.x < 32) {
-            double mf = 0.0;
-            for (int b = lane; b < nblk; b += 32) mf = fmax(mf, R.red[(size_t)b * 4 + 3]);
-            for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
-            if (lane == 0) S.ctl[3] = mf;
-        }
-#pragma unroll
-        for (int k = 0; k < R2_STAGE / R2_THREADS; ++k) {
-            const int i = threadIdx.x + k * R2_THREADS;
-            if (i < ne) { S.epos[i] = pv[k]; S.edir[i] = dv[k]; }
-        }
-        if ((int)threadIdx.x < nf16) *reinterpret_cast<uint4*>(S.eflag + 16 * threadIdx.x) = fv;
-        e_fresh = true;
-    };
-    // candidate sums, argmin, x_np, partial reductions; returns after the barrier that publishes x_np
-    auto line_search = [&]() {
+    // One line search.  With `decide` the call first settles, from the max|F|^2 of the PREVIOUS line search, whether there is a
+    // line search at all (2DGrowth.py:131-140,162-164): the partials are requested at the start of the energy phase and read
+    // at its end, so the control step costs no L2 round trip and no block-wide synchronisation of its own -- the energy
+    // phase runs speculatively (it only writes scratch) and the call returns 1 (converged), 2 (restart: stalled or out of
+    // bounds) or 3 (line-search cap) BEFORE anything is published.  Returns 0 after a complete line search.
+    auto line_search = [&](bool decide) -> int {
         const double dscale = (double)scale;
         const double inv_step = 1.0 / (20.0 * dscale);
         const double2* pos = R.pos[cur];
@@ -973,14 +946,15 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         const int* oidx = R.oidx[cs];
         // ---------------- E
         unsigned long long t_blk = (R.debug == 8 && threadIdx.x == 0) ? gtimer() : 0ull;
+        double mfv[5];                          // this lane's share of the max|F|^2 partials (grids have at most 160 blocks)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int b = lane + 32 * i;
+            mfv[i] = (decide && warp == 0 && b < nblk) ? R.red[(size_t)b * 4 + 3] : 0.0;
+        }
         if (er.emax > er.emin && !e_fresh) {            // first line of a pass: nothing was requested ahead
-#if KMC_R2_ETMA
             if (e_inflight) { mbar_wait(&S.mbar_e, e_parity); e_parity ^= 1u; }
             issue_e(pos, sdir);
-#else
-            load_e(pos, sdir, false);
-            __syncthreads();
-#endif
         }
         if (blockIdx.x == 0) {          // ordered list of mover slots
             const int T = blockDim.x, t = threadIdx.x;
@@ -1023,11 +997,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             EOperands O;
             O.pos = pos; O.dir = sdir; O.flag = R.flag; O.sub = R.sub.sxy;
             if (er.emax > er.emin) {
-#if KMC_R2_ETMA
                 mbar_wait(&S.mbar_e, e_parity);
                 e_parity ^= 1u;
                 e_inflight = false;
-#endif
                 e_fresh = false;
                 O.pos = S.epos - er.emin; O.dir = S.edir - er.emin; O.flag = S.eflag - er.emin;
             }
@@ -1059,7 +1031,26 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             const double v = group_sum<32>(acc[a]);
             if (lane == 0) wrow[KC + a] = v;
         }
+        if (decide && warp == 0) {
+            double mf = fmax(fmax(fmax(mfv[0], mfv[1]), fmax(mfv[2], mfv[3])), mfv[4]);
+            for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+            if (lane == 0) S.ctl[3] = mf;
+        }
         __syncthreads();
+        if (decide) {       // every block, identical arithmetic: the order of the tests is the reference's
+            const double mF = S.ctl[3];
+            maxF = mF;
+            int code = 0;
+            if (stall_check && fabs(lastmaxF - mF) < 1e-8) code = 2;         // :162-164 relaxation stalled
+            else {
+                lastmaxF = mF;
+                stall_check = true;
+                if (!(mF > threshold)) code = 1;                             // :131 converged
+                else if (R.max_ls > 0 && ls >= R.max_ls) code = 3;
+                else if (S.ctl[2] > P.Dmax) code = 2;                        // :137-140 atom out of bounds
+            }
+            if (code) return code;
+        }
         if (threadIdx.x < R2_NE) {
             double v = 0.0;
             for (int w = 0; w < R2_THREADS / 32; ++w) v += S.u.e.wred[w][threadIdx.x];
@@ -1212,21 +1203,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(6)
         // the next line search (if there is one) starts from x_np with the directions and flags just published: request
         // its operands now, the copies land while the control arithmetic runs
-#if KMC_R2_ETMA
         if (er.emax > er.emin) issue_e(R.pos[cur ^ 1], R.sdir[cs]);
-        const bool maxf_done = false;
-#else
-        const bool maxf_done = er.emax > er.emin;
-        if (maxf_done) load_e(R.pos[cur ^ 1], R.sdir[cs], true);
-#endif
-        if (!maxf_done && threadIdx.x < 32) {
-            double mf = 0.0;
-            for (int b = lane; b < nblk; b += 32) mf = fmax(mf, R.red[(size_t)b * 4 + 3]);
-            for (int o = 16; o > 0; o >>= 1) mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
-            if (lane == 0) S.ctl[3] = mf;
-        }
-        __syncthreads();
         ++ls;
+        return 0;
     };
 
     for (;;) {                                                         // one pass == one (recursive) call of Relaxation
@@ -1260,21 +1239,17 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             layout_x0 = true;
         }
         relax2_barrier(R, epoch);
-        line_search();                                                  // :121-129
+        int code = line_search(false);                                  // :121-129
         if (overflow) { status = -4; break; }
-        maxF = S.ctl[3];
-        lastmaxF = maxF;
-        bool restart = false;
-        while (maxF > threshold) {                                      // :131
-            if (R.max_ls > 0 && ls >= R.max_ls) { status = -6; break; }
-            if (S.ctl[2] > P.Dmax) { restart = true; break; }           // :137-140
+        stall_check = false;                                            // lastmaxF = maxF after the first line search (:130)
+        for (;;) {
             cur ^= 1;                                                   // x_n <- x_np ; s_n already updated in phase G  (:147-150)
-            line_search();                                              // :152-160
+            code = line_search(true);                                   // :131-160, the exit tests included
+            if (code) { cur ^= 1; break; }                              // no line search happened: x_np stays where it was
             if (overflow) { status = -4; break; }
-            maxF = S.ctl[3];
-            if (fabs(lastmaxF - maxF) < 1e-8) { restart = true; break; }    // :162-164
-            lastmaxF = maxF;
         }
+        if (code == 3) status = -6;
+        const bool restart = code == 2;
         if (status != 0 || !restart) break;
         ++restarts;
         scale *= 2;
