@@ -192,6 +192,28 @@ int kmc_hop_place(KmcCtx* ctx, const KmcBins* sbins, int64_t k, double u);
 int kmc_event(KmcCtx* ctx, const KmcBins* sbins, double u0, double u1, int64_t max_line_searches,
               int32_t* kind_out, int64_t* hop_k_out, double* rtot_out, KmcRelaxStats* stats);
 
+/* The event above is queued on the context's stream as ONE chain of kernels (rate table, selection, placement decided
+ * on the device, relaxation) with a single host synchronisation at its end.  kmc_set_event_mode(ctx, 0) selects the
+ * first-generation host-stepped placement instead (same results; cross-check).  The split form lets one host thread
+ * advance several replicas (one context each) concurrently: enqueue all, then finish all. */
+int kmc_set_event_mode(KmcCtx* ctx, int mode);
+int kmc_event_enqueue(KmcCtx* ctx, const KmcBins* sbins, double u0, double u1, int64_t max_line_searches);
+int kmc_event_finish(KmcCtx* ctx, int32_t* kind_out, int64_t* hop_k_out, double* rtot_out, KmcRelaxStats* stats);
+/* 1: the enqueued event has completed (kmc_event_finish returns at once), 0: still running, < 0: error */
+int kmc_event_ready(KmcCtx* ctx);
+/* temperature x flux sweeps (BASELINE configs[3]; per-replica constants: Constants.py:45-46, 2DGrowth.py:43): one event
+ * of each of R replicas, all queued before the first is waited for.  Arrays have R entries; rc_out[r] = status of
+ * replica r.  Returns the first non-zero status other than KMC_E_ITERCAP, else 0. */
+int kmc_events_batch(KmcCtx** ctxs, KmcBins** sbins, int32_t R, const double* u0, const double* u1, int64_t max_line_searches,
+                     int32_t* kind_out, int64_t* hop_k_out, double* rtot_out, KmcRelaxStats* stats, int32_t* rc_out);
+
+/* Measurement helpers (bench.py).  kmc_fp64_peak: non-tensor FP64 FMA rate of the device in TFLOP/s (register-resident
+ * DFMA chains at full occupancy, best of `repeats` runs, CUDA events) -- the denominator of the pair kernels' FP-pipe
+ * roofline.  kmc_relax_diag: counters of the context's last relaxation: out[0] re-sorts of the
+ * cell-sorted state, out[1] movers summed over its line searches, out[2] work items, out[3] reserved. */
+int kmc_fp64_peak(KmcCtx* ctx, int32_t repeats, double* tflops_out, double* ms_out);
+int kmc_relax_diag(KmcCtx* ctx, int64_t out[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,6 +133,38 @@ def HopAtom(i, adatoms, substrate_bins, u=None, max_line_searches=0, stats=None)
     return ctx.state_get()
 
 
+def LocalRelaxation(adatoms, substrate_bins, around, max_line_searches=0, stats=None):
+    """2DGrowth.py:168-199 (defined by the reference, never called by its loop): the adatoms of the 3x3(+seam) stencil
+    around `around` are taken out of the array (highest index first), relaxed ON THEIR OWN with scale=4, appended again;
+    when the largest squared force of the whole configuration then exceeds 1e-3 a global Relaxation(scale=4) follows.
+    Host logic over the device primitives (NearbyAtoms, Relaxation, forces), operation for operation -- including the
+    reference's index lookup by exact zero distance (:185) and its repeated deletes for duplicated stencil entries."""
+    adatoms = np.asarray(adatoms, dtype=np.float64)
+    ctx = runtime.context()
+    adatom_bins = Bins.PutInBins(adatoms)                                                   # :182
+    nearby = np.asarray(Bins.NearbyAtoms(around[0], around[1], adatom_bins))                # :183
+    idx = []
+    if nearby.size:
+        D = np.asarray(Periodic.Distances(nearby, adatoms))                                 # :184
+        idx = [int(np.nonzero(row == 0)[0][0]) for row in D]
+    relaxing = []
+    for i in sorted(idx, reverse=True):                                                     # :185-190
+        relaxing.append(adatoms[2 * i])
+        relaxing.append(adatoms[2 * i + 1])
+        adatoms = np.delete(adatoms, 2 * i)
+        adatoms = np.delete(adatoms, 2 * i)
+    relaxing = np.array(relaxing)
+    relaxing = Relaxation(relaxing, substrate_bins, scale=4, max_line_searches=max_line_searches, stats=stats)   # :192
+    adatoms = np.append(adatoms, relaxing)                                                  # :193
+    if adatoms.size == 0:
+        return adatoms
+    F = np.asarray(Energy.AdatomAdatomForces(adatoms)) + np.asarray(Energy.AdatomSubstrateForces(adatoms, substrate_bins))   # :194
+    maxF = float(np.max(F[0::2] ** 2 + F[1::2] ** 2))                                       # :195 (max over atoms of |F_i|^2)
+    if maxF > 1e-3:                                                                         # :196-198
+        adatoms = Relaxation(adatoms, substrate_bins, scale=4, threshold=1e-4, max_line_searches=max_line_searches, stats=stats)
+    return adatoms
+
+
 def IslandStatistics(adatoms, gv=None):
     """Islands = connected components of the adatoms under the reference's bond rule d < 1.2 r_a with the
     x-periodic minimum image (Bins.py:100, Periodic.py:27-36).  Analysis helper (host side, not on the hot path):
@@ -175,6 +207,24 @@ class Simulation(object):
         self.t = 0
         self.time = 0.0          # physical KMC clock (extension: the reference only counts events, 2DGrowth.py:316,343)
         self.log = []
+        self.rate_mode, self.rate_threshold, self.relax_mode, self.select_mode, self.event_mode = 0, 0.0, 2, 0, 1
+        self.restored = None
+
+    def set_modes(self, rate_mode=None, rate_threshold=None, relax_mode=None, select_mode=None, event_mode=None):
+        """engine knobs (kmc_set_rate_mode / _relax_mode / _select_mode / _event_mode); remembered for checkpoints"""
+        if rate_mode is not None or rate_threshold is not None:
+            self.rate_mode = self.rate_mode if rate_mode is None else int(rate_mode)
+            self.rate_threshold = self.rate_threshold if rate_threshold is None else float(rate_threshold)
+            self.ctx.set_rate_mode(self.rate_mode, self.rate_threshold)
+        if relax_mode is not None:
+            self.relax_mode = int(relax_mode)
+            self.ctx.set_relax_mode(self.relax_mode)
+        if select_mode is not None:
+            self.select_mode = int(select_mode)
+            self.ctx.set_select_mode(self.select_mode)
+        if event_mode is not None:
+            self.event_mode = int(event_mode)
+            self.ctx.set_event_mode(self.event_mode)
 
     @property
     def adatoms(self):
@@ -196,22 +246,73 @@ class Simulation(object):
         self.log.append(rec)
         return rec
 
-    def save(self, path):
-        """checkpoint: positions, substrate, constants, counters (npz)"""
+    # ---- state I/O -----------------------------------------------------------------
+    @staticmethod
+    def _npz(path):
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"
+
+    def save(self, path, rng=None, uniforms=None, uniform_pos=0):
+        """Checkpoint (npz; '.npz' is appended when missing, here and in load): positions, substrate, constants,
+        counters, the engine's mode knobs, and the random state -- Python's `random` state (what step() draws from
+        when no uniforms are passed, 2DGrowth.py:76,248,322), optionally a numpy Generator `rng` and/or an explicit
+        uniform stream with its read position -- so that a resumed run continues the SAME trajectory."""
+        import pickle
         p = self.params
-        np.savez_compressed(path, adatoms=self.adatoms, substrate=self.substrate, t=self.t, time=self.time,
-                            params=np.array([getattr(p, f) for f, _ in p._fields_], dtype=np.float64))
+        extra = {}
+        if rng is not None:
+            extra["np_rng"] = np.frombuffer(pickle.dumps(rng.bit_generator.state), dtype=np.uint8)
+        if uniforms is not None:
+            extra["uniforms"] = np.asarray(uniforms, dtype=np.float64)
+        np.savez_compressed(self._npz(path), adatoms=self.adatoms, substrate=self.substrate, t=self.t, time=self.time,
+                            params=np.array([getattr(p, f) for f, _ in p._fields_], dtype=np.float64),
+                            modes=np.array([self.rate_mode, self.relax_mode, self.select_mode, self.event_mode], dtype=np.int64),
+                            rate_threshold=self.rate_threshold, uniform_pos=int(uniform_pos),
+                            py_random=np.frombuffer(pickle.dumps(random.getstate()), dtype=np.uint8), **extra)
 
     @classmethod
-    def load(cls, path, device=None):
+    def load(cls, path, device=None, restore_random=True):
+        """-> Simulation; `sim.restored` holds dict(np_rng=Generator or None, uniforms=array or None, uniform_pos=int)"""
+        import pickle
         from ._lib import KmcParams
-        z = np.load(path)
+        z = np.load(cls._npz(path))
         p = KmcParams()
         for (f, ct), v in zip(p._fields_, z["params"]):
             setattr(p, f, int(v) if "int" in ct.__name__ else float(v))
         sim = cls(adatoms=z["adatoms"], substrate=z["substrate"], device=device, params=p)
         sim.t, sim.time = int(z["t"]), float(z["time"])
+        if "modes" in z.files:
+            rate_mode, relax_mode, select_mode, event_mode = (int(v) for v in z["modes"])
+            sim.set_modes(rate_mode=rate_mode, rate_threshold=float(z["rate_threshold"]), relax_mode=relax_mode,
+                          select_mode=select_mode, event_mode=event_mode)
+        if restore_random and "py_random" in z.files:
+            random.setstate(pickle.loads(z["py_random"].tobytes()))
+        rng = None
+        if "np_rng" in z.files:
+            rng = np.random.default_rng()
+            rng.bit_generator.state = pickle.loads(z["np_rng"].tobytes())
+        sim.restored = {"np_rng": rng, "uniforms": z["uniforms"] if "uniforms" in z.files else None,
+                        "uniform_pos": int(z["uniform_pos"]) if "uniform_pos" in z.files else 0}
         return sim
+
+    def dump_frame(self, path, forces=True):
+        """The data of the reference's per-event frames (2DGrowth.py:332-341: atoms + bin grid, PlotAtoms/PlotSubstrate :259-279;
+        force-coloured atoms, PlotStresses :290-300) as an npz instead of a PNG (matplotlib is not part of the hot path):
+        adatoms, substrate, surface flags, per-atom forces F_aa + F_as and |F|, the bin grid lines, t."""
+        ad = self.adatoms
+        n = ad.size // 2
+        out = {"t": self.t, "adatoms": ad, "substrate": self.substrate}
+        p = self.params
+        out["bin_edges_x"] = -p.L / 2 + p.bin_size * np.arange(p.nbins_x + 1)
+        out["bin_edges_y"] = p.Dmin + p.bin_size * np.arange(p.nbins_y + 1)
+        if n:
+            out["is_surface"] = np.asarray(self.ctx.rates(ad, self.sbins)["is_surface"])
+            if forces:
+                F = np.asarray(self.ctx.forces(ad, self.sbins, 3))
+                out["forces"] = F
+                out["force_norm"] = np.sqrt(F[0::2] ** 2 + F[1::2] ** 2)        # the colour of PlotStresses
+        np.savez_compressed(self._npz(path), **out)
+        return self._npz(path)
 
     def close(self):
         self.sbins.close()

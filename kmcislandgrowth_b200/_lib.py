@@ -83,6 +83,14 @@ SIGNATURES = {
     "kmc_hop_place": (C.c_int, [_VP, _VP, _I64, _D]),
     "kmc_event": (C.c_int, [_VP, _VP, _D, _D, _I64, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_D),
                             C.POINTER(KmcRelaxStats)]),
+    "kmc_set_event_mode": (C.c_int, [_VP, C.c_int]),
+    "kmc_event_enqueue": (C.c_int, [_VP, _VP, _D, _D, _I64]),
+    "kmc_event_finish": (C.c_int, [_VP, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_D), C.POINTER(KmcRelaxStats)]),
+    "kmc_event_ready": (C.c_int, [_VP]),
+    "kmc_events_batch": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP), _I32, C.POINTER(_D), C.POINTER(_D), _I64, C.POINTER(_I32),
+                                   C.POINTER(_I64), C.POINTER(_D), C.POINTER(KmcRelaxStats), C.POINTER(_I32)]),
+    "kmc_fp64_peak": (C.c_int, [_VP, _I32, C.POINTER(_D), C.POINTER(_D)]),
+    "kmc_relax_diag": (C.c_int, [_VP, C.POINTER(_I64)]),
 }
 
 _LIB = None

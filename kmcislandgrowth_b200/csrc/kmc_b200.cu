@@ -1,125 +1,40 @@
 // kmc_b200.cu -- host side of libkmcb200.so: context, device buffers, kernel launches, C-ABI.
 // See include/kmc_b200.h for the contract of every entry point and the reference lines it replaces.
-#include "../../include/kmc_b200.h"
+// (The persistent relaxation kernels live in kmc_relax1.cu / kmc_relax2.cu, the on-device event path in kmc_event.cu.)
+#include "kmc_host.h"
 #include "kmc_kernels.cuh"
-#include "kmc_line.cuh"
-#include "kmc_relax.cuh"
-#include "kmc_relax2.cuh"
+#include "kmc_line_kernels.cuh"
 
 #include <cmath>
-#include <cstdarg>
 #include <algorithm>
-#include <cstdio>
 #include <cstring>
 #include <map>
-#include <string>
-#include <vector>
 
 using namespace kmc;
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int kmc_fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
 }
+#define fail kmc_fail
 
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t _e = (call);                                                                         \
-        if (_e != cudaSuccess)                                                                           \
-            return fail(KMC_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
-    } while (0)
-
-#define TRY(expr)              \
-    do {                       \
-        int _rc = (expr);      \
-        if (_rc != 0) return _rc; \
-    } while (0)
-
-// ------------------------------------------------------------------------------------ buffers
-struct DBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-struct KmcBins {
-    int64_t n = 0;
-    int ncell2 = 0;
-    double2* xy = nullptr;     // original order
-    int* cell_of = nullptr;    // [n]
-    int* start = nullptr;      // [ncell+2]
-    double2* sxy = nullptr;    // [n]
-    int* sidx = nullptr;       // [n]
-};
-
-struct TimingRec {
-    int family;
-    cudaEvent_t a, b;
-};
-
-struct KmcCtx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    KmcParams hp{};
-    DevParams dp{};
-    std::vector<DBuf> slots;        // scratch, indexed by small integers
-    int64_t launches = 0;
-    bool timing = false;
-    std::vector<TimingRec> recs;
-    std::vector<std::string> families;
-    // pinned mailbox for small readbacks
-    void* h_mail = nullptr;
-    // trajectory state
-    double* st_xy = nullptr;
-    int64_t st_n = 0, st_cap = 0;
-    int relax_mode = 2;             // 2: persistent kernel on cell-sorted state (default), 1: first-generation persistent kernel, 0: host-driven loop
-    size_t item_cap = 0;
-    // incremental rate table (kmc_rates_update): cached per-atom results and the positions they were computed at
-    int rate_mode = 0;              // 0: full sweep per event (default, parity mode); 1: kmc_event uses kmc_rates_update
-    double rate_threshold = 0.0;    // displacement (Angstrom) below which a neighbourhood counts as unchanged; 0 = exact
-    double2* rc_xy = nullptr;
-    double* rc_rate = nullptr;
-    double* rc_du = nullptr;
-    uint8_t* rc_surf = nullptr;
-    double2* rc_pending = nullptr;  // positions of removed atoms whose neighbourhood must be refreshed
-    int rc_npending = 0;
-    int64_t rc_cap = 0, rc_n = 0, rc_last = 0;
-    bool rc_valid = false;
-    int select_mode = 0;            // 0: sequential-order sums up to 65536 atoms, block scan beyond; 1: always sequential; 2: always block scan
-    int sm_count = 148;
-};
-
-enum Slot {
-    S_IN0 = 0, S_IN1, S_IN2, S_IN3, S_OUT0, S_OUT1, S_OUT2, S_OUT3, S_OUT4, S_OUT5, S_OUT6, S_OUT7,
-    S_CELLOF, S_START, S_CURSOR, S_SXY, S_SIDX, S_PARTIAL, S_DONE, S_CAND, S_E, S_CTRL,
-    S_F, S_FAA, S_FAS, S_X0, S_XN, S_XNP, S_SN, S_TMP0, S_TMP1, S_TMP2, S_TMP3,
-    S_FLAG, S_MOVERS, S_NMOV, S_LPART, S_FIX, S_AMIN, S_RED, S_SYNC,
-    S_POS0, S_POS1, S_SD0, S_SD1, S_OI0, S_OI1, S_KEY, S_PERM, S_CHUNKS, S_ITEMS, S_NBR, S_COUNT
-};
-
-static int ensure(KmcCtx* c, DBuf& b, size_t bytes) {
+int kmc_ensure(KmcCtx* c, DBuf& b, size_t bytes) {
     if (bytes <= b.cap && b.p) return 0;
     if (b.p) {
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaFree(b.p));
         b.p = nullptr;
+        b.cap = 0;
     }
     size_t want = bytes + bytes / 2 + 256;
     CK(cudaMalloc(&b.p, want));
     b.cap = want;
-    return 0;
-}
-
-template <class T>
-static int slot(KmcCtx* c, int id, size_t count, T** out) {
-    TRY(ensure(c, c->slots[id], (count > 0 ? count : 1) * sizeof(T)));
-    *out = (T*)c->slots[id].p;
     return 0;
 }
 
@@ -132,8 +47,9 @@ struct Pending {
 struct Call {
     KmcCtx* c;
     int mem;
+    DevGuard guard;
     std::vector<Pending> outs;
-    Call(KmcCtx* ctx, int m) : c(ctx), mem(m) {}
+    Call(KmcCtx* ctx, int m) : c(ctx), mem(m), guard(ctx) {}
     template <class T>
     int in(const T* p, size_t count, int slot_id, const T** dev) {
         if (mem == KMC_DEVICE || p == nullptr) { *dev = p; return 0; }
@@ -162,41 +78,20 @@ struct Call {
 };
 
 // ------------------------------------------------------------------------------------ launches
-static int family_id(KmcCtx* c, const char* name) {
+int kmc_family_id(KmcCtx* c, const char* name) {
     for (size_t i = 0; i < c->families.size(); ++i)
         if (c->families[i] == name) return (int)i;
     c->families.push_back(name);
     return (int)c->families.size() - 1;
 }
 
-struct LaunchScope {
-    KmcCtx* c;
-    TimingRec rec{};
-    bool on;
-    LaunchScope(KmcCtx* ctx, const char* fam) : c(ctx), on(ctx->timing) {
-        c->launches++;
-        if (on) {
-            rec.family = family_id(c, fam);
-            cudaEventCreate(&rec.a);
-            cudaEventCreate(&rec.b);
-            cudaEventRecord(rec.a, c->stream);
-        }
-    }
-    ~LaunchScope() {
-        if (on) {
-            cudaEventRecord(rec.b, c->stream);
-            c->recs.push_back(rec);
-        }
-    }
-};
-
-#define LAUNCH(ctx, fam, kernel, grid, block, ...)                      \
-    do {                                                                \
-        LaunchScope _ls((ctx), (fam));                                  \
-        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);     \
-    } while (0)
-
-static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+// timing events are recycled: kmc_timing_reset returns them to the pool instead of destroying them
+cudaEvent_t kmc_event_from_pool(KmcCtx* c) {
+    cudaEvent_t e = nullptr;
+    if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
 
 static DevParams to_dev(const KmcParams& p) {
     DevParams d{};
@@ -252,14 +147,8 @@ static int build_cells(KmcCtx* c, const double2* d_xy, int n, int B, int* cell_o
     return 0;
 }
 
-static CellView view_of(const KmcBins* b) {
-    CellView v;
-    v.start = b->start; v.sxy = b->sxy; v.sidx = b->sidx; v.n = (int)b->n;
-    return v;
-}
-
 // scratch cell lists for B configurations of the adatoms
-static int scratch_cells(KmcCtx* c, const double2* d_xy, int n, int B, CellView* out) {
+int kmc_scratch_cells(KmcCtx* c, const double2* d_xy, int n, int B, CellView* out) {
     const int ncell2 = c->dp.ncell + 2;
     int *cell_of, *start, *cursor, *sidx;
     double2* sxy;
@@ -351,14 +240,14 @@ static int line_energies_dev(KmcCtx* c, const double2* d_x, const double2* d_s, 
 
 static int adatom_view(KmcCtx* c, const double2* d_xy, int n, int B, bool need_cells, CellView* v) {
     if (c->dp.aa_mode == 0 && !need_cells) { *v = identity_view(d_xy, n); return 0; }
-    return scratch_cells(c, d_xy, n, B, v);
+    return kmc_scratch_cells(c, d_xy, n, B, v);
 }
 
-static int rates_dev(KmcCtx* c, const double2* d_xy, int n, const KmcBins* sb, double* rate, uint8_t* surf, double* du,
+int kmc_rates_dev(KmcCtx* c, const double2* d_xy, int n, const KmcBins* sb, double* rate, uint8_t* surf, double* du,
                      double* ua, double* ul, int* na, int* ns) {
     if (n == 0) return 0;
     CellView ad;
-    TRY(scratch_cells(c, d_xy, n, 1, &ad));
+    TRY(kmc_scratch_cells(c, d_xy, n, 1, &ad));
     const int G = pick_group(n);
     const unsigned grid = cdiv((size_t)n * G, 256);
     CellView sub = view_of(sb);
@@ -374,31 +263,34 @@ static int rates_dev(KmcCtx* c, const double2* d_xy, int n, const KmcBins* sb, d
 
 // ---- incremental rate table ------------------------------------------------------------------------------
 constexpr int RC_PENDING = 64;
-static int mail(KmcCtx* c, const void* dev, size_t bytes);
 static int rc_reserve(KmcCtx* c, int64_t n) {
     if (n <= c->rc_cap && c->rc_xy) return 0;
     const int64_t cap = std::max<int64_t>(n + n / 2, 1024);
-    double2* xy; double* rate; double* du; uint8_t* surf;
+    double2* xy = nullptr; double* rate = nullptr; double* du = nullptr; uint8_t* surf = nullptr;
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMalloc(&xy, sizeof(double2) * (size_t)cap));
-    CK(cudaMalloc(&rate, sizeof(double) * (size_t)cap));
-    CK(cudaMalloc(&du, sizeof(double) * (size_t)cap));
-    CK(cudaMalloc(&surf, (size_t)cap));
-    if (c->rc_xy) {
-        CK(cudaMemcpy(xy, c->rc_xy, sizeof(double2) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(rate, c->rc_rate, sizeof(double) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(du, c->rc_du, sizeof(double) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(surf, c->rc_surf, (size_t)c->rc_n, cudaMemcpyDeviceToDevice));
-        cudaFree(c->rc_xy); cudaFree(c->rc_rate); cudaFree(c->rc_du); cudaFree(c->rc_surf);
+    cudaError_t e = cudaMalloc(&xy, sizeof(double2) * (size_t)cap);
+    if (e == cudaSuccess) e = cudaMalloc(&rate, sizeof(double) * (size_t)cap);
+    if (e == cudaSuccess) e = cudaMalloc(&du, sizeof(double) * (size_t)cap);
+    if (e == cudaSuccess) e = cudaMalloc(&surf, (size_t)cap);
+    if (e == cudaSuccess && !c->rc_pending) e = cudaMalloc(&c->rc_pending, sizeof(double2) * RC_PENDING);
+    if (e == cudaSuccess && c->rc_xy) {
+        e = cudaMemcpy(xy, c->rc_xy, sizeof(double2) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(rate, c->rc_rate, sizeof(double) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(du, c->rc_du, sizeof(double) * (size_t)c->rc_n, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(surf, c->rc_surf, (size_t)c->rc_n, cudaMemcpyDeviceToDevice);
     }
-    if (!c->rc_pending) CK(cudaMalloc(&c->rc_pending, sizeof(double2) * RC_PENDING));
+    if (e != cudaSuccess) {       // nothing half-allocated survives a failure; the old tables stay valid
+        cudaFree(xy); cudaFree(rate); cudaFree(du); cudaFree(surf);
+        return fail(KMC_E_CUDA, "rate-table cache of %lld atoms: %s", (long long)cap, cudaGetErrorString(e));
+    }
+    if (c->rc_xy) { cudaFree(c->rc_xy); cudaFree(c->rc_rate); cudaFree(c->rc_du); cudaFree(c->rc_surf); }
     c->rc_xy = xy; c->rc_rate = rate; c->rc_du = du; c->rc_surf = surf; c->rc_cap = cap;
     return 0;
 }
 
 // the cached tables follow the index changes of the trajectory state: HopAtom deletes entry k and appends the moved atom
 // (2DGrowth.py:241,255), DepositAdatom appends (:93).  A new atom has no cached entry (NaN reference position).
-static int rc_on_remove(KmcCtx* c, int k) {
+int kmc_rc_on_remove(KmcCtx* c, int k) {
     if (!c->rc_valid) return 0;
     const int n = (int)c->rc_n;
     if (c->rc_npending >= RC_PENDING) { c->rc_valid = false; return 0; }
@@ -420,25 +312,23 @@ static int rc_on_remove(KmcCtx* c, int k) {
     c->rc_n = n - 1;
     return 0;
 }
-static int rc_on_append(KmcCtx* c) {
+int kmc_rc_on_append(KmcCtx* c) {
     if (!c->rc_valid) return 0;
     TRY(rc_reserve(c, c->rc_n + 1));
-    const double nan2[2] = {std::nan(""), std::nan("")};
-    CK(cudaMemcpyAsync(c->rc_xy + c->rc_n, nan2, sizeof(nan2), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));       // nan2 lives on the stack
+    CK(cudaMemsetAsync(c->rc_xy + c->rc_n, 0xFF, sizeof(double2), c->stream));      // all-ones bit pattern == NaN: "no cached entry"
     c->rc_n++;
     return 0;
 }
 
 // bring the cached rate table up to date with the trajectory state; returns the number of atoms recomputed
-static int rates_update_impl(KmcCtx* c, const KmcBins* sb, double threshold, int64_t* recomputed) {
+int kmc_rates_update_impl(KmcCtx* c, const KmcBins* sb, double threshold, int64_t* recomputed) {
     const int n = (int)c->st_n;
     *recomputed = 0;
     if (n == 0) { c->rc_n = 0; c->rc_valid = true; c->rc_npending = 0; return 0; }
     TRY(rc_reserve(c, n));
     const bool full = !c->rc_valid || c->rc_n != n || c->dp.aa_mode == 0;      // all-pairs U_appx: every rate depends on every atom
     if (full) {
-        TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, c->rc_rate, c->rc_surf, c->rc_du, nullptr, nullptr, nullptr, nullptr));
+        TRY(kmc_rates_dev(c, (const double2*)c->st_xy, n, sb, c->rc_rate, c->rc_surf, c->rc_du, nullptr, nullptr, nullptr, nullptr));
         CK(cudaMemcpyAsync(c->rc_xy, c->st_xy, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
         c->rc_n = n; c->rc_valid = true; c->rc_npending = 0;
         *recomputed = n;
@@ -455,7 +345,7 @@ static int rates_update_impl(KmcCtx* c, const KmcBins* sb, double threshold, int
     LAUNCH(c, "rates_mark", k_rates_mark, cdiv(std::max(n, c->rc_npending), 256), 256, c->dp, (const double2*)c->st_xy, (const double2*)c->rc_xy, n,
            threshold * threshold, (const double2*)c->rc_pending, c->rc_npending, dirty_cell, self_dirty);
     CellView ad;
-    TRY(scratch_cells(c, (const double2*)c->st_xy, n, 1, &ad));
+    TRY(kmc_scratch_cells(c, (const double2*)c->st_xy, n, 1, &ad));
     const int G = pick_group(n);
     const unsigned grid = cdiv((size_t)n * G, 256);
     CellView sub = view_of(sb);
@@ -470,14 +360,14 @@ static int rates_update_impl(KmcCtx* c, const KmcBins* sb, double threshold, int
     }
 #undef RATES_MASKED
     CK(cudaGetLastError());
-    TRY(mail(c, counter, sizeof(unsigned long long)));
+    TRY(kmc_mail(c, counter, sizeof(unsigned long long)));
     *recomputed = (int64_t) * (const unsigned long long*)c->h_mail;
     c->rc_last = *recomputed;
     c->rc_npending = 0;
     return 0;
 }
 
-static int state_reserve(KmcCtx* c, int64_t n) {
+int kmc_state_reserve(KmcCtx* c, int64_t n) {
     if (n <= c->st_cap) return 0;
     int64_t cap = std::max<int64_t>(n + n / 2, 1024);
     double* p;
@@ -493,9 +383,28 @@ static int state_reserve(KmcCtx* c, int64_t n) {
 }
 
 // read `bytes` from device memory into the pinned mailbox and wait
-static int mail(KmcCtx* c, const void* dev, size_t bytes) {
+int kmc_mail(KmcCtx* c, const void* dev, size_t bytes) {
     CK(cudaMemcpyAsync(c->h_mail, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// 2DGrowth.py:319-324 on device pointers; the mode switch of kmc_set_select_mode applies to kmc_select AND kmc_event
+int kmc_select_dev(KmcCtx* c, const double* dr, const uint8_t* dsf, int n, double u, long long* dres, double* drt, double* dpj) {
+    const bool parallel = !dpj && (c->select_mode == 2 || (c->select_mode == 0 && n > 65536));
+    if (parallel) {
+        const int nblocks = (int)std::min<int64_t>(1024, ((int64_t)n + 4095) / 4096);
+        const int chunk = (int)(((int64_t)n + nblocks - 1) / nblocks);
+        double* bsum;
+        int* bcount;
+        TRY(slot(c, S_TMP2, (size_t)nblocks, &bsum));
+        TRY(slot(c, S_TMP3, (size_t)nblocks, &bcount));
+        LAUNCH(c, "select", k_select_block_sums, nblocks, 1024, dr, dsf, n, chunk, bsum, bcount);
+        LAUNCH(c, "select", k_select_final, 1, 1024, c->dp, dr, dsf, n, chunk, nblocks, bsum, bcount, u, dres, drt);
+    } else {
+        LAUNCH(c, "select", k_select, 1, 32, c->dp, dr, dsf, n, u, dres, drt, dpj);
+    }
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -513,7 +422,10 @@ int kmc_create(const KmcParams* p, int device, KmcCtx** out) {
     if (e != cudaSuccess || ndev == 0)
         return fail(KMC_E_NODEVICE, "no CUDA device available (%s); libkmcb200 has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(KMC_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     CK(cudaSetDevice(device));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     const int sm_count = prop.multiProcessorCount;
@@ -527,25 +439,30 @@ int kmc_create(const KmcParams* p, int device, KmcCtx** out) {
     if (const char* e = getenv("KMC_RELAX_MODE")) c->relax_mode = (strcmp(e, "host") == 0) ? 0 : (strcmp(e, "persistent1") == 0 ? 1 : 2);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(KMC_E_CUDA, "cudaStreamCreate failed"); }
     c->own_stream = true;
-    if (cudaMallocHost(&c->h_mail, 4096) != cudaSuccess) { delete c; return fail(KMC_E_CUDA, "cudaMallocHost failed"); }
-    if (cudaMalloc(&c->slots[S_DONE].p, 65536 * sizeof(unsigned)) != cudaSuccess) { delete c; return fail(KMC_E_CUDA, "cudaMalloc failed"); }
+    if (cudaMallocHost(&c->h_mail, 4096) != cudaSuccess) { kmc_destroy(c); return fail(KMC_E_CUDA, "cudaMallocHost failed"); }
+    if (cudaMalloc(&c->slots[S_DONE].p, 65536 * sizeof(unsigned)) != cudaSuccess) { kmc_destroy(c); return fail(KMC_E_CUDA, "cudaMalloc failed"); }
     c->slots[S_DONE].cap = 65536 * sizeof(unsigned);
     cudaMemset(c->slots[S_DONE].p, 0, c->slots[S_DONE].cap);
+    if (cudaMalloc(&c->st_n_dev, 64) != cudaSuccess) { kmc_destroy(c); return fail(KMC_E_CUDA, "cudaMalloc failed"); }
+    cudaMemset(c->st_n_dev, 0, 64);
+    if (const char* e = getenv("KMC_EVENT_MODE")) c->event_mode = atoi(e) ? 1 : 0;
     *out = c;
     return 0;
 }
 
 int kmc_destroy(KmcCtx* c) {
     if (!c) return 0;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    DevGuard guard(c);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& b : c->slots) if (b.p) cudaFree(b.p);
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& e : c->event_pool) cudaEventDestroy(e);
     if (c->st_xy) cudaFree(c->st_xy);
+    if (c->st_n_dev) cudaFree(c->st_n_dev);
     if (c->rc_xy) { cudaFree(c->rc_xy); cudaFree(c->rc_rate); cudaFree(c->rc_du); cudaFree(c->rc_surf); }
     if (c->rc_pending) cudaFree(c->rc_pending);
     if (c->h_mail) cudaFreeHost(c->h_mail);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
@@ -566,6 +483,7 @@ int kmc_get_params(KmcCtx* c, KmcParams* p) {
 
 int kmc_set_stream(KmcCtx* c, void* s) {
     if (!c) return fail(KMC_E_ARG, "ctx is NULL");
+    DevGuard guard(c);
     CK(cudaStreamSynchronize(c->stream));
     if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)s;
@@ -574,6 +492,7 @@ int kmc_set_stream(KmcCtx* c, void* s) {
 
 int kmc_synchronize(KmcCtx* c) {
     if (!c) return fail(KMC_E_ARG, "ctx is NULL");
+    DevGuard guard(c);
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -588,14 +507,16 @@ int kmc_timing_enable(KmcCtx* c, int on) {
 
 int kmc_timing_reset(KmcCtx* c) {
     if (!c) return fail(KMC_E_ARG, "ctx is NULL");
+    DevGuard guard(c);
     CK(cudaStreamSynchronize(c->stream));
-    for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& r : c->recs) { c->event_pool.push_back(r.a); c->event_pool.push_back(r.b); }      // recycled, not destroyed
     c->recs.clear();
     return 0;
 }
 
 int kmc_timing_read(KmcCtx* c, const char* family, double* total_ms, int64_t* launches) {
     if (!c) return fail(KMC_E_ARG, "ctx is NULL");
+    DevGuard guard(c);
     CK(cudaStreamSynchronize(c->stream));
     double tot = 0;
     int64_t cnt = 0;
@@ -673,6 +594,7 @@ int kmc_bin_index(KmcCtx* c, const double* xy, int64_t n, int32_t* out, int mem)
 int kmc_bins_create(KmcCtx* c, const double* xy, int64_t n, int mem, KmcBins** out) {
     if (!c || !out) return fail(KMC_E_ARG, "NULL argument");
     if (n < 0 || n > (1ll << 30)) return fail(KMC_E_ARG, "bad atom count");
+    DevGuard guard(c);
     KmcBins* b = new KmcBins();
     b->n = n;
     b->ncell2 = c->dp.ncell + 2;
@@ -684,17 +606,23 @@ int kmc_bins_create(KmcCtx* c, const double* xy, int64_t n, int mem, KmcBins** o
         kmc_bins_destroy(c, b);
         return fail(KMC_E_CUDA, "cudaMalloc failed for a cell list of %lld atoms", (long long)n);
     }
-    if (n > 0)
-        CK(cudaMemcpyAsync(b->xy, xy, sizeof(double2) * (size_t)n, mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-    TRY(slot(c, S_CURSOR, (size_t)b->ncell2, &cursor));
-    TRY(build_cells(c, b->xy, (int)n, 1, b->cell_of, b->start, cursor, b->sidx, b->sxy));
-    if (mem == KMC_HOST) CK(cudaStreamSynchronize(c->stream));
+    auto body = [&]() -> int {
+        if (n > 0)
+            CK(cudaMemcpyAsync(b->xy, xy, sizeof(double2) * (size_t)n, mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        TRY(slot(c, S_CURSOR, (size_t)b->ncell2, &cursor));
+        TRY(build_cells(c, b->xy, (int)n, 1, b->cell_of, b->start, cursor, b->sidx, b->sxy));
+        if (mem == KMC_HOST) CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    const int rc = body();
+    if (rc != 0) { kmc_bins_destroy(c, b); return rc; }       // no half-built cell list leaks
     *out = b;
     return 0;
 }
 
 int kmc_bins_destroy(KmcCtx* c, KmcBins* b) {
     if (!b) return 0;
+    DevGuard guard(c);
     if (c) cudaStreamSynchronize(c->stream);
     cudaFree(b->xy); cudaFree(b->cell_of); cudaFree(b->start); cudaFree(b->sxy); cudaFree(b->sidx);
     delete b;
@@ -705,6 +633,7 @@ int64_t kmc_bins_count(const KmcBins* b) { return b ? b->n : 0; }
 
 int kmc_bins_export(KmcCtx* c, const KmcBins* b, int32_t* cell_of, int32_t* cell_start, double* sorted_xy, int32_t* sorted_idx, int mem) {
     if (!c || !b) return fail(KMC_E_ARG, "NULL argument");
+    DevGuard guard(c);
     cudaMemcpyKind k = mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (cell_of && b->n) CK(cudaMemcpyAsync(cell_of, b->cell_of, sizeof(int) * (size_t)b->n, k, c->stream));
     if (cell_start) CK(cudaMemcpyAsync(cell_start, b->start, sizeof(int) * (size_t)b->ncell2, k, c->stream));
@@ -756,7 +685,7 @@ int kmc_neighbors(KmcCtx* c, const double* xy, int64_t n, const KmcBins* sb, int
         if (dso) CK(cudaMemsetAsync(dso, 0, sizeof(long long), c->stream));
         return call.finish();
     }
-    TRY(rates_dev(c, (const double2*)d, (int)n, sb, nullptr, nullptr, nullptr, nullptr, nullptr, dna, dns));
+    TRY(kmc_rates_dev(c, (const double2*)d, (int)n, sb, nullptr, nullptr, nullptr, nullptr, nullptr, dna, dns));
     CellView ad;   // cell list built by rates_dev lives in the scratch slots
     ad.start = (int*)c->slots[S_START].p; ad.sxy = (double2*)c->slots[S_SXY].p; ad.sidx = (int*)c->slots[S_SIDX].p; ad.n = (int)n;
     if (dao) {
@@ -823,7 +752,7 @@ int kmc_line_energies(KmcCtx* c, const double* xy, const double* dir, int64_t n,
     TRY(call.out(e_out, (size_t)K, S_OUT0, &de));
     if (K == KC && n > 0) {      // the line-search engine: one cell list, 20 candidates per pair in registers
         CellView ad;
-        TRY(scratch_cells(c, (const double2*)dx, (int)n, 1, &ad));
+        TRY(kmc_scratch_cells(c, (const double2*)dx, (int)n, 1, &ad));
         TRY(line_energies_dev(c, (const double2*)dx, (const double2*)ds, (int)n, (double)scale, ad, sb, de, nullptr));
         return call.finish();
     }
@@ -864,7 +793,7 @@ int kmc_probe(KmcCtx* c, const double* probes, int64_t m, const double* xy, int6
     TRY(call.out(min_d_a, (size_t)m, S_OUT2, &d2));
     TRY(call.out(min_d_s, (size_t)m, S_OUT3, &d3));
     CellView ad = identity_view(nullptr, 0);
-    if (n > 0) TRY(scratch_cells(c, (const double2*)dx, (int)n, 1, &ad));
+    if (n > 0) TRY(kmc_scratch_cells(c, (const double2*)dx, (int)n, 1, &ad));
     LAUNCH(c, "probe", k_probe, cdiv((size_t)m * 32, 128), 128, c->dp, (const double2*)dp, (int)m, ad, view_of(sb), d0, d1, d2, d3);
     CK(cudaGetLastError());
     return call.finish();
@@ -887,7 +816,7 @@ int kmc_rates(KmcCtx* c, const double* xy, int64_t n, const KmcBins* sb, double*
     TRY(call.out(ul, (size_t)n, S_OUT4, &d_ul));
     TRY(call.out(na, (size_t)n, S_OUT5, &d_na));
     TRY(call.out(ns, (size_t)n, S_OUT6, &d_ns));
-    TRY(rates_dev(c, (const double2*)d, (int)n, sb, d_rate, d_surf, d_du, d_ua, d_ul, d_na, d_ns));
+    TRY(kmc_rates_dev(c, (const double2*)d, (int)n, sb, d_rate, d_surf, d_du, d_ua, d_ul, d_na, d_ns));
     return call.finish();
 }
 
@@ -904,27 +833,16 @@ int kmc_select(KmcCtx* c, const double* rate, const uint8_t* surf, int64_t n, do
     TRY(call.out((long long*)result, 2, S_OUT0, &dres));
     TRY(call.out(rtot, 1, S_OUT1, &drt));
     TRY(call.out(pj, (size_t)n + 1, S_OUT2, &dpj));
-    const bool parallel = !pj && (c->select_mode == 2 || (c->select_mode == 0 && n > 65536));
-    if (parallel) {
-        const int nblocks = (int)std::min<int64_t>(1024, (n + 4095) / 4096);
-        const int chunk = (int)((n + nblocks - 1) / nblocks);
-        double* bsum;
-        int* bcount;
-        TRY(slot(c, S_TMP2, (size_t)nblocks, &bsum));
-        TRY(slot(c, S_TMP3, (size_t)nblocks, &bcount));
-        LAUNCH(c, "select", k_select_block_sums, nblocks, 1024, dr, dsf, (int)n, chunk, bsum, bcount);
-        LAUNCH(c, "select", k_select_final, 1, 1024, c->dp, dr, dsf, (int)n, chunk, nblocks, bsum, bcount, u, dres, drt);
-    } else {
-        LAUNCH(c, "select", k_select, 1, 32, c->dp, dr, dsf, (int)n, u, dres, drt, dpj);
-    }
-    CK(cudaGetLastError());
+    TRY(kmc_select_dev(c, dr, dsf, (int)n, u, dres, drt, dpj));
     return call.finish();
 }
 
 // ---------------------------------------------------------------- trajectory state + events
 int kmc_state_set(KmcCtx* c, const double* xy, int64_t n, int mem) {
     if (!c || (n > 0 && !xy)) return fail(KMC_E_ARG, "NULL argument");
-    TRY(state_reserve(c, n + 1));
+    if (c->ev_pending) return fail(KMC_E_ARG, "an enqueued event has not been finished (kmc_event_finish)");
+    DevGuard guard(c);
+    TRY(kmc_state_reserve(c, n + 1));
     if (n > 0)
         CK(cudaMemcpyAsync(c->st_xy, xy, sizeof(double) * 2 * (size_t)n, mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     c->st_n = n;
@@ -935,6 +853,8 @@ int kmc_state_set(KmcCtx* c, const double* xy, int64_t n, int mem) {
 
 int kmc_state_move(KmcCtx* c, const double* xy, int64_t n, int mem) {
     if (!c || (n > 0 && !xy)) return fail(KMC_E_ARG, "NULL argument");
+    if (c->ev_pending) return fail(KMC_E_ARG, "an enqueued event has not been finished (kmc_event_finish)");
+    DevGuard guard(c);
     if (n != c->st_n) return fail(KMC_E_ARG, "kmc_state_move: %lld positions for a state of %lld atoms (same atoms, new positions)", (long long)n, (long long)c->st_n);
     if (n > 0)
         CK(cudaMemcpyAsync(c->st_xy, xy, sizeof(double) * 2 * (size_t)n, mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
@@ -944,6 +864,8 @@ int kmc_state_move(KmcCtx* c, const double* xy, int64_t n, int mem) {
 
 int kmc_state_get(KmcCtx* c, double* xy, int64_t cap, int64_t* n_out, int mem) {
     if (!c) return fail(KMC_E_ARG, "ctx is NULL");
+    if (c->ev_pending) return fail(KMC_E_ARG, "an enqueued event has not been finished (kmc_event_finish)");
+    DevGuard guard(c);
     if (n_out) *n_out = c->st_n;
     if (!xy) return 0;
     if (cap < c->st_n) return fail(KMC_E_CAPACITY, "state holds %lld atoms, capacity %lld", (long long)c->st_n, (long long)cap);
@@ -993,7 +915,7 @@ static int relax_host_driven(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
         TRY(forces_dev(c, ad, &ctrl->amin, sb, n, nullptr, nullptr, (double2*)F));
         LAUNCH(c, "relax_reduce", k_relax_reduce, 1, 1024, cand, xbase, (const double2*)F, n, ctrl, xnp);
         CK(cudaGetLastError());
-        TRY(mail(c, ctrl, sizeof(RelaxCtrl)));
+        TRY(kmc_mail(c, ctrl, sizeof(RelaxCtrl)));
         st.line_searches++;
         return 0;
     };
@@ -1037,224 +959,16 @@ static int relax_host_driven(KmcCtx* c, const KmcBins* sb, int32_t scale0, doubl
     return 0;
 }
 
-}  // extern "C"
-
-// 2DGrowth.py:97-166 as one persistent cooperative kernel (kmc_relax.cuh)
-template <int G>
-static int launch_relax(KmcCtx* c, RelaxArgs& R, int blocks) {
-    void* args[] = {(void*)&R};
-    c->launches++;
-    cudaEvent_t ea = nullptr, eb = nullptr;
-    if (c->timing) { cudaEventCreate(&ea); cudaEventCreate(&eb); cudaEventRecord(ea, c->stream); }
-    CK(cudaLaunchCooperativeKernel((const void*)k_relax_persistent<G>, dim3(blocks), dim3(256), args, 0, c->stream));
-    if (c->timing) { cudaEventRecord(eb, c->stream); c->recs.push_back({family_id(c, "relax_persistent"), ea, eb}); }
-    return 0;
-}
-
-static int relax_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, double threshold0, int64_t max_ls, KmcRelaxStats* stats) {
-    KmcRelaxStats st{};
-    const int n = (int)c->st_n;
-    if (n == 0) { if (stats) *stats = st; return 0; }
-    RelaxArgs R{};
-    R.P = c->dp; R.sub = view_of(sb); R.n = n; R.ncell2 = c->dp.ncell + 2;
-    // grid: all SMs x 2 blocks for large systems, fewer blocks (cheaper barriers) for small ones
-    int blocks = std::min(2 * c->sm_count, std::max(1, (n * 32 + 255) / 256));
-    const int gthreads = blocks * 256;
-    int G = 32;
-    while (G > 1 && (long long)n * G > gthreads) G >>= 1;
-    R.x0 = (double2*)c->st_xy;
-    TRY(slot(c, S_XN, (size_t)n, &R.xn));
-    TRY(slot(c, S_XNP, (size_t)n, &R.xnp));
-    TRY(slot(c, S_SN, (size_t)n, &R.sn));
-    TRY(slot(c, S_F, (size_t)n, &R.F));
-    TRY(slot(c, S_CELLOF, (size_t)n, &R.cell_of));
-    TRY(slot(c, S_START, (size_t)R.ncell2, &R.start));
-    TRY(slot(c, S_CURSOR, (size_t)R.ncell2, &R.cursor));
-    TRY(slot(c, S_SIDX, (size_t)n, &R.sidx));
-    TRY(slot(c, S_SXY, (size_t)n, &R.sxy));
-    TRY(slot(c, S_FLAG, (size_t)n, &R.flag));
-    TRY(slot(c, S_MOVERS, (size_t)n, &R.movers));
-    TRY(slot(c, S_NMOV, 4, &R.n_movers));
-    TRY(slot(c, S_LPART, (size_t)std::max(blocks, LINE_BLOCKS) * KC, &R.partial));
-    TRY(slot(c, S_FIX, (size_t)n * KC, &R.fix));
-    TRY(slot(c, S_RED, (size_t)blocks * 4, &R.red));
-    unsigned char* sync;
-    TRY(slot(c, S_SYNC, 256, &sync));
-    CK(cudaMemsetAsync(sync, 0, 256, c->stream));
-    R.barrier = (unsigned int*)sync;
-    R.need_rebuild = (int*)(sync + 16);
-    R.pair_counter = (unsigned long long*)(sync + 32);
-    R.stats = (KmcRelaxStatsDev*)(sync + 64);
-    R.phase_ns = (unsigned long long*)(sync + 128);
-    R.scale0 = scale0; R.threshold0 = threshold0; R.max_ls = max_ls;
-    switch (G) {
-        case 32: TRY(launch_relax<32>(c, R, blocks)); break;
-        case 16: TRY(launch_relax<16>(c, R, blocks)); break;
-        case 8: TRY(launch_relax<8>(c, R, blocks)); break;
-        case 4: TRY(launch_relax<4>(c, R, blocks)); break;
-        case 2: TRY(launch_relax<2>(c, R, blocks)); break;
-        default: TRY(launch_relax<1>(c, R, blocks)); break;
-    }
-    TRY(mail(c, sync, 256));
-    if (getenv("KMC_PHASE_TIMING")) {
-        const unsigned long long* ph = (const unsigned long long*)((const char*)c->h_mail + 128);
-        const KmcRelaxStatsDev* d0 = (const KmcRelaxStatsDev*)((const char*)c->h_mail + 64);
-        const double nls = d0->line_searches > 0 ? (double)d0->line_searches : 1.0;
-        fprintf(stderr, "[kmc phase us/ls] energy %.2f | bar %.2f | fix+bar %.2f | sums+xnp %.2f | bar %.2f | forces %.2f | bar %.2f | ctl+update+bar %.2f  (ls=%lld blocks=%d G=%d)\n",
-                ph[0] / nls * 1e-3, ph[1] / nls * 1e-3, ph[2] / nls * 1e-3, ph[3] / nls * 1e-3, ph[4] / nls * 1e-3, ph[5] / nls * 1e-3, ph[6] / nls * 1e-3, ph[7] / nls * 1e-3,
-                (long long)d0->line_searches, blocks, G);
-    }
-    const unsigned long long visits = *(const unsigned long long*)((const char*)c->h_mail + 32);
-    const KmcRelaxStatsDev* ds = (const KmcRelaxStatsDev*)((const char*)c->h_mail + 64);
-    st.line_searches = ds->line_searches; st.restarts = ds->restarts; st.maxF = ds->maxF;
-    st.final_threshold = ds->final_threshold; st.final_scale = ds->final_scale; st.status = ds->status;
-    // ordered pair visits of one energy sweep x 20 candidates x line searches
-    const long long per_sweep = (long long)visits + (c->dp.aa_mode == 0 ? (long long)n * (n - 1) / 2 : 0);
-    st.pair_evals = st.line_searches * KC * per_sweep;
-    if (stats) *stats = st;
-    if (st.status != 0) return fail(st.status, "relaxation stopped at the line-search cap (%lld)", (long long)max_ls);
-    return 0;
-}
-
-// second-generation persistent kernel (kmc_relax2.cuh): cell-sorted state, balanced work items
-static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
-    void* args[] = {(void*)&R};
-    c->launches++;
-    cudaEvent_t ea = nullptr, eb = nullptr;
-    if (c->timing) { cudaEventCreate(&ea); cudaEventCreate(&eb); cudaEventRecord(ea, c->stream); }
-    static bool smem_set = false;        // the kernel's shared state (staged operands) exceeds the 48 KB static limit
-    if (!smem_set) {
-        CK(cudaFuncSetAttribute((const void*)k_relax2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
-        smem_set = true;
-    }
-    if (R.sync_mode == 0) {
-        CK(cudaLaunchCooperativeKernel((const void*)k_relax2, dim3(blocks), dim3(R2_THREADS), args, sizeof(Relax2Smem), c->stream));
-    } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(R2_THREADS); cfg.dynamicSmemBytes = sizeof(Relax2Smem); cfg.stream = c->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = blocks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, k_relax2, R));
-    }
-    if (c->timing) { cudaEventRecord(eb, c->stream); c->recs.push_back({family_id(c, "relax_persistent"), ea, eb}); }
-    return 0;
-}
-
-static int relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, double threshold0, int64_t max_ls, KmcRelaxStats* stats) {
-    KmcRelaxStats st{};
-    const int n = (int)c->st_n;
-    if (n == 0) { if (stats) *stats = st; return 0; }
-    // launch shape: one block (<= 16 adatoms), one cluster of <= 8 blocks (<= 256 adatoms), else one block per SM
-    int blocks = std::min(c->sm_count, std::max(1, (n + 15) / 16));
-    int sync_mode = 0;
-    if (blocks == 1) sync_mode = 1;
-    else if (n <= 256 && !getenv("KMC_NO_CLUSTER")) { blocks = std::min(blocks, 8); sync_mode = 2; }
-    const int G = 0;
-    if (c->item_cap == 0) c->item_cap = (size_t)n * 4 + (size_t)c->dp.ncell * 2 + 1024;
-    if (const char* e = getenv("KMC_ITEM_CAP")) c->item_cap = (size_t)std::max(1, atoi(e));      // tests: force the grow-and-relaunch path
-    for (int attempt = 0; attempt < 8; ++attempt) {
-        Relax2Args R{};
-        R.P = c->dp; R.sub = view_of(sb); R.n = n; R.ncell2 = c->dp.ncell + 2;
-        R.x0 = (double2*)c->st_xy;
-        TRY(slot(c, S_POS0, (size_t)n, &R.pos[0]));
-        TRY(slot(c, S_POS1, (size_t)n, &R.pos[1]));
-        TRY(slot(c, S_SD0, (size_t)n, &R.sdir[0]));
-        TRY(slot(c, S_SD1, (size_t)n, &R.sdir[1]));
-        TRY(slot(c, S_OI0, (size_t)n, &R.oidx[0]));
-        TRY(slot(c, S_OI1, (size_t)n, &R.oidx[1]));
-        TRY(slot(c, S_CELLOF, (size_t)n, &R.cellof));
-        TRY(slot(c, S_NBR, (size_t)n * 4, &R.nbr));
-        TRY(slot(c, S_FLAG, (size_t)n + 32, &R.flag));        // the staged flag copy reads whole 16-byte groups
-        TRY(slot(c, S_START, (size_t)R.ncell2, &R.start));
-        TRY(slot(c, S_CURSOR, (size_t)R.ncell2, &R.cursor));
-        TRY(slot(c, S_KEY, (size_t)n, &R.key));
-        TRY(slot(c, S_PERM, (size_t)n, &R.perm));
-        TRY(slot(c, S_CHUNKS, (size_t)c->dp.ncell * R2_PARTS + 2, &R.chunks));
-        TRY(slot(c, S_ITEMS, c->item_cap, &R.items));
-        R.item_cap = (int)c->item_cap;
-        TRY(slot(c, S_MOVERS, (size_t)n, &R.movers));
-        TRY(slot(c, S_LPART, (size_t)std::max(blocks, LINE_BLOCKS) * R2_NE, &R.partial));
-        TRY(slot(c, S_FIX, (size_t)n * KC, &R.fix));
-        TRY(slot(c, S_RED, (size_t)blocks * 4, &R.red));
-        unsigned char* sync;
-        TRY(slot(c, S_SYNC, 512, &sync));
-        CK(cudaMemsetAsync(sync, 0, 512, c->stream));
-        R.barrier = (unsigned int*)sync;
-        R.hist = (unsigned long long*)(sync + 256);
-        R.blk_ns = nullptr;
-        R.need_rebuild = (int*)(sync + 16);
-        R.n_items = (int*)(sync + 20);
-        R.n_movers = (int*)(sync + 24);
-        R.pair_counter = (unsigned long long*)(sync + 32);
-        R.stats = (KmcRelaxStatsDev*)(sync + 64);
-        R.phase_ns = (unsigned long long*)(sync + 128);
-        R.scale0 = scale0; R.threshold0 = threshold0; R.max_ls = max_ls;
-        R.sync_mode = sync_mode;
-        R.debug = getenv("KMC_DEBUG_E") ? atoi(getenv("KMC_DEBUG_E")) : 0;
-        R.phase_block = !getenv("KMC_PHASE_TIMING") ? -1 : (getenv("KMC_PHASE_BLOCK") ? std::min(atoi(getenv("KMC_PHASE_BLOCK")), blocks - 1) : 0);
-        if (R.debug == 8) {      // diagnostics: per-block phase times (borrows the mover fix-up buffer's tail: n*KC doubles >> 2*blocks)
-            TRY(slot(c, S_TMP3, (size_t)2 * blocks, &R.blk_ns));
-            CK(cudaMemsetAsync(R.blk_ns, 0, sizeof(unsigned long long) * 2 * blocks, c->stream));
-        }
-        TRY(launch_relax2(c, R, blocks));
-        if (R.debug == 8) {
-            std::vector<unsigned long long> h(2 * blocks);
-            CK(cudaMemcpyAsync(h.data(), R.blk_ns, sizeof(unsigned long long) * 2 * blocks, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            for (int ph = 0; ph < 2; ++ph) {
-                double mn = 1e30, mx = 0, sum = 0; int arg = 0;
-                for (int b = (blocks > 1 ? 1 : 0); b < blocks; ++b) { const double v = (double)h[2 * b + ph]; sum += v; if (v < mn) mn = v; if (v > mx) { mx = v; arg = b; } }
-                fprintf(stderr, "[kmc2 per-block %s ns total] min %.0f mean %.0f max %.0f (block %d) block0 %.0f :", ph ? "G" : "E", mn, sum / std::max(1, blocks - 1), mx, arg, (double)h[ph]);
-                for (int b = 0; b < blocks; b += 7) fprintf(stderr, " %.0f", (double)h[2 * b + ph] * 1e-3);
-                fprintf(stderr, "\n");
-            }
-        }
-        TRY(mail(c, sync, 512));
-        const char* hm = (const char*)c->h_mail;
-        if (R.debug == 7) {     // diagnostics: per-atom displacement over a whole line (19/20/scale*|s|), decades from 1e-6 A
-            const unsigned long long* h = (const unsigned long long*)(hm + 256);
-            fprintf(stderr, "[kmc2 disp hist]");
-            for (int k = 0; k < 16; ++k) fprintf(stderr, " %llu", h[k]);
-            fprintf(stderr, "\n");
-        }
-        const KmcRelaxStatsDev* ds = (const KmcRelaxStatsDev*)(hm + 64);
-        if (ds->status == -4) {            // work list overflow: grow and run again (x0 is untouched)
-            const int need = *(const int*)(hm + 20);
-            c->item_cap = (size_t)need + need / 2 + 1024;
-            continue;
-        }
-        const unsigned long long visits = *(const unsigned long long*)(hm + 32);
-        if (getenv("KMC_PHASE_TIMING")) {
-            const unsigned long long* ph = (const unsigned long long*)(hm + 128);
-            const double nls = ds->line_searches > 0 ? (double)ds->line_searches : 1.0;
-            fprintf(stderr, "[kmc2 E detail us/ls] control %.2f | items %.2f | reduce+store %.2f\n", ph[32] / nls * 1e-3, ph[33] / nls * 1e-3, ph[0] / nls * 1e-3);
-            fprintf(stderr, "[kmc2 G detail us/ls] beta-reduce %.2f | rebuild-check %.2f | ranges+copy wait %.2f | adatom sweep %.2f | substrate sweep %.2f | group sums %.2f | update+flags %.2f | block max+store %.2f\n", ph[10] / nls * 1e-3, ph[11] / nls * 1e-3, ph[34] / nls * 1e-3, ph[12] / nls * 1e-3, ph[13] / nls * 1e-3, ph[14] / nls * 1e-3, ph[15] / nls * 1e-3, ph[5] / nls * 1e-3);
-            fprintf(stderr, "[kmc2 phase us/ls] E %.2f | bar %.2f | fix+bar %.2f | S %.2f | bar %.2f | G %.2f | bar %.2f | rebuild %.2f (%.1f us each, %lld) movers/ls %.1f (ls=%lld restarts=%lld blocks=%d G=%d items=%d)\n",
-                    (ph[0] + ph[32] + ph[33]) / nls * 1e-3, ph[1] / nls * 1e-3, ph[2] / nls * 1e-3, ph[3] / nls * 1e-3, ph[4] / nls * 1e-3, (ph[5] + ph[34] + ph[10] + ph[11] + ph[12] + ph[13] + ph[14] + ph[15]) / nls * 1e-3,
-                    ph[6] / nls * 1e-3, ph[7] / nls * 1e-3, ph[8] ? ph[7] * 1e-3 / ph[8] : 0.0, (long long)ph[8], ph[9] / nls, (long long)ds->line_searches, (long long)ds->restarts, blocks, G, *(const int*)(hm + 20));
-        }
-        st.line_searches = ds->line_searches; st.restarts = ds->restarts; st.maxF = ds->maxF;
-        st.final_threshold = ds->final_threshold; st.final_scale = ds->final_scale; st.status = ds->status;
-        const long long per_sweep = (long long)visits + (c->dp.aa_mode == 0 ? (long long)n * (n - 1) / 2 : 0);
-        st.pair_evals = st.line_searches * KC * per_sweep;
-        if (stats) *stats = st;
-        if (st.status != 0) return fail(st.status, "relaxation stopped at the line-search cap (%lld)", (long long)max_ls);
-        return 0;
-    }
-    return fail(KMC_E_CAPACITY, "relaxation work list kept overflowing");
-}
-
-extern "C" {
 
 int kmc_relax(KmcCtx* c, const KmcBins* sb, int32_t scale0, double threshold0, int64_t max_ls, KmcRelaxStats* stats) {
     if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
     if (scale0 < 1 || !(threshold0 > 0)) return fail(KMC_E_ARG, "bad scale0 / threshold0");
-    TRY(state_reserve(c, c->st_n + 1));
+    if (c->ev_pending) return fail(KMC_E_ARG, "an enqueued event has not been finished (kmc_event_finish)");
+    DevGuard guard(c);
+    TRY(kmc_state_reserve(c, c->st_n + 1));
     if (c->relax_mode == 0) return relax_host_driven(c, sb, scale0, threshold0, max_ls, stats);
-    if (c->relax_mode == 2) return relax2_persistent(c, sb, scale0, threshold0, max_ls, stats);
-    return relax_persistent(c, sb, scale0, threshold0, max_ls, stats);
+    if (c->relax_mode == 2) return kmc_relax2_persistent(c, sb, scale0, threshold0, max_ls, stats);
+    return kmc_relax_persistent1(c, sb, scale0, threshold0, max_ls, stats);
 }
 
 int kmc_set_relax_mode(KmcCtx* c, int mode) {
@@ -1280,8 +994,9 @@ int kmc_set_rate_mode(KmcCtx* c, int mode, double threshold) {
 int kmc_rates_update(KmcCtx* c, const KmcBins* sb, double threshold, double* rate, uint8_t* surf, double* du, int64_t* recomputed, int mem) {
     if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
     if (!(threshold >= 0.0)) return fail(KMC_E_ARG, "threshold must be >= 0");
+    DevGuard guard(c);
     int64_t redone = 0;
-    TRY(rates_update_impl(c, sb, threshold, &redone));
+    TRY(kmc_rates_update_impl(c, sb, threshold, &redone));
     if (recomputed) *recomputed = redone;
     const size_t n = (size_t)c->st_n;
     const cudaMemcpyKind kind = mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -1294,16 +1009,16 @@ int kmc_rates_update(KmcCtx* c, const KmcBins* sb, double threshold, double* rat
     return 0;
 }
 
-int kmc_deposit_place(KmcCtx* c, const KmcBins* sb, double u) {
-    if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
+// host-stepped placement (event mode 0): the first-generation path, kept as a cross-check of the device-resident one
+static int deposit_place_host(KmcCtx* c, const KmcBins* sb, double u) {
     const int n = (int)c->st_n;
-    TRY(state_reserve(c, n + 1));
+    TRY(kmc_state_reserve(c, n + 1));
     double ref_y = 0.0;                                                           // :73-75
     double* tmp;
     TRY(slot(c, S_TMP0, 8, &tmp));
     if (n > 0) {
         LAUNCH(c, "misc_min_y", k_min_y, 1, 1024, (const double2*)c->st_xy, n, c->hp.deposit_mode ? 1 : 0, tmp);
-        TRY(mail(c, tmp, sizeof(double)));
+        TRY(kmc_mail(c, tmp, sizeof(double)));
         ref_y = *(const double*)c->h_mail;
     }
     // :76  new_x = PutInBox(u*L) (host arithmetic identical to the reference's, Periodic.py:8-20)
@@ -1316,7 +1031,7 @@ int kmc_deposit_place(KmcCtx* c, const KmcBins* sb, double u) {
     }
     double new_y = 2 * c->hp.r_as + ref_y;                                        // :77
     CellView ad = identity_view(nullptr, 0);
-    if (n > 0) TRY(scratch_cells(c, (const double2*)c->st_xy, n, 1, &ad));        // :78
+    if (n > 0) TRY(kmc_scratch_cells(c, (const double2*)c->st_xy, n, 1, &ad));        // :78
     // :80-92 -- the probe descends by r_a/2 until it is close to something; 64 heights per launch
     const int M = 64;
     double *probes, *dmin_a, *dmin_s;
@@ -1339,7 +1054,7 @@ int kmc_deposit_place(KmcCtx* c, const KmcBins* sb, double u) {
                 CK(cudaMemcpyAsync(c->st_xy + 2 * (size_t)n, pos, sizeof(pos), cudaMemcpyHostToDevice, c->stream));   // :93
                 CK(cudaStreamSynchronize(c->stream));
                 c->st_n = n + 1;
-                TRY(rc_on_append(c));
+                TRY(kmc_rc_on_append(c));
                 return 0;
             }
         }
@@ -1400,19 +1115,19 @@ static int hop_place_impl(KmcCtx* c, const KmcBins* sb, int64_t k, double u, con
     // :239 SurfaceAtoms of the current state; kmc_event has just computed the same flags for the rate table
     const uint8_t* surf = surface_flags;
     if (!surf) {
-        TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, nullptr, own, nullptr, nullptr, nullptr, nullptr, nullptr));
+        TRY(kmc_rates_dev(c, (const double2*)c->st_xy, n, sb, nullptr, own, nullptr, nullptr, nullptr, nullptr, nullptr));
         surf = own;
     }
     LAUNCH(c, "hop_target", k_hop_target, 1, 1024, c->dp, (const double2*)c->st_xy, surf, n, (int)k, u, tmp);          // :240-248
     CK(cudaGetLastError());
-    TRY(mail(c, tmp, 3 * sizeof(double)));
+    TRY(kmc_mail(c, tmp, 3 * sizeof(double)));
     const double* hm = (const double*)c->h_mail;
     if (hm[0] < 1) return fail(KMC_E_NOCANDIDATE, "HopAtom: no surface atom within 3 r_a of adatom %lld", (long long)k);
     const double tx = hm[1], ty = hm[2];
     double* rest;
     TRY(slot(c, S_XN, (size_t)2 * n, &rest));
     LAUNCH(c, "misc_remove", k_remove_atom, cdiv(n, 256), 256, (const double2*)c->st_xy, n, (int)k, (double2*)rest);   // :241
-    TRY(rc_on_remove(c, (int)k));
+    TRY(kmc_rc_on_remove(c, (int)k));
     double hp[12];
     for (int i = 0; i < 6; ++i) {                                                 // :249-251
         const double t = i * M_PI / 3;
@@ -1425,7 +1140,7 @@ static int hop_place_impl(KmcCtx* c, const KmcBins* sb, int64_t k, double u, con
     TRY(slot(c, S_TMP3, 64, &eas));
     CK(cudaMemcpyAsync(probes, hp, sizeof(hp), cudaMemcpyHostToDevice, c->stream));
     CellView ad = identity_view(nullptr, 0);
-    if (n - 1 > 0) TRY(scratch_cells(c, (const double2*)rest, n - 1, 1, &ad));
+    if (n - 1 > 0) TRY(kmc_scratch_cells(c, (const double2*)rest, n - 1, 1, &ad));
     LAUNCH(c, "probe", k_probe, cdiv(6 * 32, 128), 128, c->dp, (const double2*)probes, 6, ad, view_of(sb), eaa, eas, nullptr, nullptr);   // :252
     CK(cudaGetLastError());
     double he[12];
@@ -1445,18 +1160,35 @@ static int hop_place_impl(KmcCtx* c, const KmcBins* sb, int64_t k, double u, con
     CK(cudaMemcpyAsync(c->st_xy, rest, sizeof(double) * 2 * (size_t)(n - 1), cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaMemcpyAsync(c->st_xy + 2 * (size_t)(n - 1), pos, sizeof(pos), cudaMemcpyHostToDevice, c->stream));   // :255
     CK(cudaStreamSynchronize(c->stream));
-    TRY(rc_on_append(c));
+    TRY(kmc_rc_on_append(c));
     return 0;
+}
+
+int kmc_deposit_place(KmcCtx* c, const KmcBins* sb, double u) {
+    if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
+    if (c->ev_pending) return fail(KMC_E_ARG, "an enqueued event has not been finished (kmc_event_finish)");
+    DevGuard guard(c);
+    if (c->event_mode == 0 || c->rate_mode == 1) return deposit_place_host(c, sb, u);
+    return kmc_deposit_place_dev(c, sb, u);
 }
 
 int kmc_hop_place(KmcCtx* c, const KmcBins* sb, int64_t k, double u) {
     if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
-    return hop_place_impl(c, sb, k, u, nullptr);
+    if (c->ev_pending) return fail(KMC_E_ARG, "an enqueued event has not been finished (kmc_event_finish)");
+    DevGuard guard(c);
+    if (c->event_mode == 0 || c->rate_mode == 1) return hop_place_impl(c, sb, k, u, nullptr);
+    return kmc_hop_place_dev(c, sb, k, u);
 }
 
 int kmc_event(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_t max_ls, int32_t* kind_out, int64_t* hop_k_out, double* rtot_out,
               KmcRelaxStats* stats) {
     if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
+    if (c->ev_pending) return fail(KMC_E_ARG, "an enqueued event has not been finished (kmc_event_finish)");
+    if (c->event_mode == 1 && c->rate_mode == 0) {      // default: the whole event is queued, ONE host synchronisation
+        TRY(kmc_event_enqueue(c, sb, u0, u1, max_ls));
+        return kmc_event_finish(c, kind_out, hop_k_out, rtot_out, stats);
+    }
+    DevGuard guard(c);
     const int n = (int)c->st_n;
     double *rate, *rt;
     uint8_t* surf;
@@ -1467,13 +1199,12 @@ int kmc_event(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_t max_ls
     TRY(slot(c, S_OUT3, 1, &rt));
     if (c->rate_mode == 1) {        // incremental table: only the neighbourhoods that changed since the last event are redone
         int64_t redone = 0;
-        TRY(rates_update_impl(c, sb, c->rate_threshold, &redone));
+        TRY(kmc_rates_update_impl(c, sb, c->rate_threshold, &redone));
         rate = c->rc_rate; surf = c->rc_surf;
     } else {
-        TRY(rates_dev(c, (const double2*)c->st_xy, n, sb, rate, surf, nullptr, nullptr, nullptr, nullptr, nullptr));   // :318
+        TRY(kmc_rates_dev(c, (const double2*)c->st_xy, n, sb, rate, surf, nullptr, nullptr, nullptr, nullptr, nullptr));   // :318
     }
-    LAUNCH(c, "select", k_select, 1, 32, c->dp, rate, surf, n, u0, res, rt, (double*)nullptr);                     // :319-324
-    CK(cudaGetLastError());
+    TRY(kmc_select_dev(c, rate, surf, n, u0, res, rt, nullptr));                                                   // :319-324
     long long hres[2];
     double hrt;
     CK(cudaMemcpyAsync(hres, res, sizeof(hres), cudaMemcpyDeviceToHost, c->stream));
@@ -1488,7 +1219,7 @@ int kmc_event(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_t max_ls
     } else {
         if (kind_out) *kind_out = 0;
         if (hop_k_out) *hop_k_out = -1;
-        TRY(kmc_deposit_place(c, sb, u1));                                        // :329
+        TRY(deposit_place_host(c, sb, u1));                                       // :329
     }
     return kmc_relax(c, sb, 16, 1e-4, max_ls, stats);                                       // :94 / :256
 }

@@ -235,4 +235,66 @@ __device__ __forceinline__ double block_max(double v, double* smem) {
 }
 __device__ __forceinline__ double block_min(double v, double* smem) { return -block_max(-v, smem); }
 
+// ---- pair terms shared by the sweep kernels, the event kernels and the relaxation kernels ----------------
+// accumulate the force of neighbour (xj,yj) on (xi,yi)
+__device__ __forceinline__ void acc_force(const DevParams& P, double xi, double yi, double2 pj, double E, double r0sq,
+                                          double& fx, double& fy) {
+    const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
+    const double dy = pj.y - yi;
+    if (P.precision == 1) {
+        const float ex = (float)dx, ey = (float)dy;
+        const float c = lj_force_coef_f32(ex * ex + ey * ey, (float)E, (float)r0sq);
+        fx += (double)(ex * c);
+        fy += (double)(ey * c);
+        return;
+    }
+    const double r2 = dx * dx + dy * dy;
+    const double c = lj_force_coef(r2, E, r0sq);
+    fx += dx * c;
+    fy += dy * c;
+}
+
+__device__ __forceinline__ double pair_energy(const DevParams& P, double xi, double yi, double2 pj, double E, double r0sq) {
+    const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
+    const double dy = pj.y - yi;
+    if (P.precision == 1) return lj_energy_f32(dx, dy, E, r0sq);
+    return lj_energy(dx * dx + dy * dy, E, r0sq);
+}
+
+// ascending sort of a short index list (cell contents keep the reference's input order, Bins.py:40-41):
+// insertion sort for the usual ~10 atoms, heapsort beyond 32
+__device__ inline void sort_indices(int* a, int m) {
+    if (m <= 32) {
+        for (int i = 1; i < m; ++i) {
+            int v = a[i], j = i - 1;
+            while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+            a[j + 1] = v;
+        }
+        return;
+    }
+    for (int start = m / 2 - 1; start >= 0; --start) {           // heapify
+        int root = start;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= m) break;
+            if (child + 1 < m && a[child] < a[child + 1]) ++child;
+            if (a[root] >= a[child]) break;
+            int t = a[root]; a[root] = a[child]; a[child] = t;
+            root = child;
+        }
+    }
+    for (int end = m - 1; end > 0; --end) {
+        int t = a[0]; a[0] = a[end]; a[end] = t;
+        int root = 0;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && a[child] < a[child + 1]) ++child;
+            if (a[root] >= a[child]) break;
+            int t2 = a[root]; a[root] = a[child]; a[child] = t2;
+            root = child;
+        }
+    }
+}
+
 }  // namespace kmc

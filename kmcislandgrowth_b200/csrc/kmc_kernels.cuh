@@ -14,7 +14,7 @@ namespace kmc {
 // =============================================================================== cell lists
 
 // Bins.py:9-22 for n points -> (nx, ny)
-__global__ void k_bin_index(DevParams P, const double2* __restrict__ xy, int n, int2* __restrict__ out) {
+static __global__ void k_bin_index(DevParams P, const double2* __restrict__ xy, int n, int2* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double2 p = xy[i];
@@ -24,7 +24,7 @@ __global__ void k_bin_index(DevParams P, const double2* __restrict__ xy, int n, 
 }
 
 // B configurations of n atoms: xy[b*n+i].  cell_of[b*n+i] = flat cell (ncell = outside); cnt[b*(ncell+2)+1+cell]++
-__global__ void k_bin_count(DevParams P, const double2* __restrict__ xy, int n, int B, int* __restrict__ cell_of,
+static __global__ void k_bin_count(DevParams P, const double2* __restrict__ xy, int n, int B, int* __restrict__ cell_of,
                             int* __restrict__ cnt) {
     const int b = blockIdx.y;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -39,7 +39,7 @@ __global__ void k_bin_count(DevParams P, const double2* __restrict__ xy, int n, 
 
 // in-place inclusive scan of cnt[b][1..ncell+1] (cnt[b][0] stays 0) -> start offsets; cursor = copy.
 // One CTA per configuration; chunked: each thread owns a contiguous chunk.
-__global__ void k_bin_scan(int ncell2 /* ncell+2 */, int* __restrict__ start, int* __restrict__ cursor) {
+static __global__ void k_bin_scan(int ncell2 /* ncell+2 */, int* __restrict__ start, int* __restrict__ cursor) {
     __shared__ int s_tot[1024];
     const int b = blockIdx.x;
     int* a = start + (size_t)b * ncell2;
@@ -72,7 +72,7 @@ __global__ void k_bin_scan(int ncell2 /* ncell+2 */, int* __restrict__ start, in
 // Pass 1: every block scans its tile of SCAN_TILE entries of a[1..m] in place (inclusive) and stores the tile total.
 // Pass 2: every block adds the sum of the totals of the tiles before it, and mirrors the result into `cursor`.
 constexpr int SCAN_TILE = 8192;
-__global__ void __launch_bounds__(1024) k_bin_scan_tiles(int m, int* __restrict__ a /* entries 1..m */, int* __restrict__ tile_tot) {
+static __global__ void __launch_bounds__(1024) k_bin_scan_tiles(int m, int* __restrict__ a /* entries 1..m */, int* __restrict__ tile_tot) {
     __shared__ int s_tot[1024];
     const int per = SCAN_TILE / 1024;
     const int lo = 1 + blockIdx.x * SCAN_TILE + threadIdx.x * per;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan_tiles(int m, int* __restrict_
     if (threadIdx.x == 1023) tile_tot[blockIdx.x] = s_tot[1023];
 }
 
-__global__ void __launch_bounds__(1024) k_bin_scan_add(int m, int* __restrict__ a, const int* __restrict__ tile_tot, int* __restrict__ cursor) {
+static __global__ void __launch_bounds__(1024) k_bin_scan_add(int m, int* __restrict__ a, const int* __restrict__ tile_tot, int* __restrict__ cursor) {
     __shared__ int s_red[32];
     __shared__ int s_base;
     int part = 0;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan_add(int m, int* __restrict__ 
 }
 
 // slot = cursor[cell]++ ; sidx[slot] = i   (order inside a cell fixed up by k_bin_order)
-__global__ void k_bin_scatter(int n, int B, int ncell2, const int* __restrict__ cell_of, int* __restrict__ cursor,
+static __global__ void k_bin_scatter(int n, int B, int ncell2, const int* __restrict__ cell_of, int* __restrict__ cursor,
                               int* __restrict__ sidx) {
     const int b = blockIdx.y;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -122,42 +122,8 @@ __global__ void k_bin_scatter(int n, int B, int ncell2, const int* __restrict__ 
 }
 
 // restore the reference's input order inside every cell (Bins.py:40-41 appends in input order) and
-// gather the positions.  One thread per cell: insertion sort for the usual ~10 atoms, heapsort beyond 32.
-__device__ inline void sort_indices(int* a, int m) {
-    if (m <= 32) {
-        for (int i = 1; i < m; ++i) {
-            int v = a[i], j = i - 1;
-            while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
-            a[j + 1] = v;
-        }
-        return;
-    }
-    for (int start = m / 2 - 1; start >= 0; --start) {           // heapify
-        int root = start;
-        for (;;) {
-            int child = 2 * root + 1;
-            if (child >= m) break;
-            if (child + 1 < m && a[child] < a[child + 1]) ++child;
-            if (a[root] >= a[child]) break;
-            int t = a[root]; a[root] = a[child]; a[child] = t;
-            root = child;
-        }
-    }
-    for (int end = m - 1; end > 0; --end) {
-        int t = a[0]; a[0] = a[end]; a[end] = t;
-        int root = 0;
-        for (;;) {
-            int child = 2 * root + 1;
-            if (child >= end) break;
-            if (child + 1 < end && a[child] < a[child + 1]) ++child;
-            if (a[root] >= a[child]) break;
-            int t2 = a[root]; a[root] = a[child]; a[child] = t2;
-            root = child;
-        }
-    }
-}
-
-__global__ void k_bin_order(int n, int B, int ncell2, const int* __restrict__ start, int* __restrict__ sidx,
+// gather the positions.  One thread per cell (sort_indices: kmc_device.cuh).
+static __global__ void k_bin_order(int n, int B, int ncell2, const int* __restrict__ start, int* __restrict__ sidx,
                             const double2* __restrict__ xy, double2* __restrict__ sxy) {
     const int b = blockIdx.y;
     const int* st = start + (size_t)b * ncell2;
@@ -171,36 +137,11 @@ __global__ void k_bin_order(int n, int B, int ncell2, const int* __restrict__ st
 
 // =============================================================================== pair sweeps
 
-// accumulate the force of neighbour (xj,yj) on (xi,yi)
-__device__ __forceinline__ void acc_force(const DevParams& P, double xi, double yi, double2 pj, double E, double r0sq,
-                                          double& fx, double& fy) {
-    const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
-    const double dy = pj.y - yi;
-    if (P.precision == 1) {
-        const float ex = (float)dx, ey = (float)dy;
-        const float c = lj_force_coef_f32(ex * ex + ey * ey, (float)E, (float)r0sq);
-        fx += (double)(ex * c);
-        fy += (double)(ey * c);
-        return;
-    }
-    const double r2 = dx * dx + dy * dy;
-    const double c = lj_force_coef(r2, E, r0sq);
-    fx += dx * c;
-    fy += dy * c;
-}
-
-__device__ __forceinline__ double pair_energy(const DevParams& P, double xi, double yi, double2 pj, double E, double r0sq) {
-    const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
-    const double dy = pj.y - yi;
-    if (P.precision == 1) return lj_energy_f32(dx, dy, E, r0sq);
-    return lj_energy(dx * dx + dy * dy, E, r0sq);
-}
-
 // Energy.py:62-75.  One group of G lanes per adatom (cell-sorted order so that a warp shares its
 // stencil); f_aa / f_as / f_sum are written at the atom's ORIGINAL index; any may be null.
 // `which_cfg` (device pointer, may be null) selects the configuration of a batch (line search winner).
 template <int G>
-__global__ void __launch_bounds__(256) k_sweep_forces(DevParams P, CellView ad_base, CellView sub, int n,
+static __global__ void __launch_bounds__(256) k_sweep_forces(DevParams P, CellView ad_base, CellView sub, int n,
                                                       const int* __restrict__ which_cfg, int ncell2,
                                                       double2* __restrict__ f_aa, double2* __restrict__ f_as,
                                                       double2* __restrict__ f_sum) {
@@ -239,7 +180,7 @@ __global__ void __launch_bounds__(256) k_sweep_forces(DevParams P, CellView ad_b
 // grid = (blocks, B).  Deterministic: per-block partials, the last block of a configuration adds them
 // in block order.  done[b] must be zero on entry and is reset on exit.
 template <int G>
-__global__ void __launch_bounds__(256) k_sweep_energy(DevParams P, CellView ad_base, CellView sub, int n, int ncell2,
+static __global__ void __launch_bounds__(256) k_sweep_energy(DevParams P, CellView ad_base, CellView sub, int n, int ncell2,
                                                       double* __restrict__ partial, unsigned int* __restrict__ done,
                                                       double* __restrict__ e_out) {
     __shared__ double s_red[32];
@@ -287,7 +228,7 @@ __global__ void __launch_bounds__(256) k_sweep_energy(DevParams P, CellView ad_b
 
 // Energy.py:121-131 TotalEnergy (unused by the driver, kept for API parity): quirky loop bounds.
 // Small-N utility: one block, all-pairs.
-__global__ void k_total_energy(DevParams P, const double2* __restrict__ xy, CellView sub, int n, double* __restrict__ e_out) {
+static __global__ void k_total_energy(DevParams P, const double2* __restrict__ xy, CellView sub, int n, double* __restrict__ e_out) {
     __shared__ double s_red[32];
     double e = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -307,7 +248,7 @@ __global__ void k_total_energy(DevParams P, const double2* __restrict__ xy, Cell
 // Energy.py:174-217 + 2DGrowth.py:46-62,201-215 for every adatom.  Bond tests use the reference's exact
 // arithmetic (dist2_exact + IEEE sqrt) so that n_a / n_s / the surface flag agree bit for bit.
 template <int G>
-__global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellView ad, CellView sub, int n,
+static __global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellView ad, CellView sub, int n,
                                                      double* __restrict__ rate, uint8_t* __restrict__ is_surface,
                                                      double* __restrict__ delta_u, double* __restrict__ u_appx_o,
                                                      double* __restrict__ u_loc_o, int* __restrict__ n_a_o,
@@ -376,7 +317,7 @@ __global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellView ad, C
 // relation "cell D is in the stencil of cell C" is symmetric (both wraps and the seam column come in pairs), so an atom
 // that moved by more than the threshold since its neighbours' rates were last computed dirties the stencil cells of its
 // old and of its new position.  `pending` = positions of atoms that were removed (HopAtom, 2DGrowth.py:241).
-__global__ void __launch_bounds__(256) k_rates_mark(DevParams P, const double2* __restrict__ xy, const double2* __restrict__ ref, int n, double thr2,
+static __global__ void __launch_bounds__(256) k_rates_mark(DevParams P, const double2* __restrict__ xy, const double2* __restrict__ ref, int n, double thr2,
                                                     const double2* __restrict__ pending, int npending, uint8_t* __restrict__ dirty_cell,
                                                     uint8_t* __restrict__ self_dirty) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,13 +354,13 @@ __global__ void __launch_bounds__(256) k_rates_mark(DevParams P, const double2* 
 
 // erase element k of an array (the cached tables follow HopAtom's np.delete, 2DGrowth.py:241)
 template <class T>
-__global__ void __launch_bounds__(256) k_erase_at(const T* __restrict__ src, int n, int k, T* __restrict__ dst) {
+static __global__ void __launch_bounds__(256) k_erase_at(const T* __restrict__ src, int n, int k, T* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n - 1) dst[i] = src[i < k ? i : i + 1];
 }
 
 // Energy.py:170-172 / :77-95 and the closeness test of 2DGrowth.py:82-90.  One warp per probe point.
-__global__ void __launch_bounds__(128) k_probe(DevParams P, const double2* __restrict__ probes, int m, CellView ad, CellView sub,
+static __global__ void __launch_bounds__(128) k_probe(DevParams P, const double2* __restrict__ probes, int m, CellView ad, CellView sub,
                                                double* __restrict__ e_aa, double* __restrict__ e_as,
                                                double* __restrict__ min_d_a, double* __restrict__ min_d_s) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -462,7 +403,7 @@ __global__ void __launch_bounds__(128) k_probe(DevParams P, const double2* __res
 // reference's sum(Rk[:i+1]) so that every pj -- and therefore the selected index -- is bit-identical
 // for the same rates and the same u.  One warp: lanes prefetch 32 rates, lane 0 owns the running sum.
 // result[0] = compacted k or -1 ; result[1] = dense index or -1 ; rtot[0] = Rd + sum.
-__global__ void k_select(DevParams P, const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, double u,
+static __global__ void k_select(DevParams P, const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, double u,
                          long long* __restrict__ result, double* __restrict__ rtot, double* __restrict__ pj_out) {
     const int lane = threadIdx.x;
     // Adding +0.0 never changes a running sum, and the dense table is zero for every non-surface atom: only the
@@ -552,7 +493,7 @@ __global__ void k_select(DevParams P, const double* __restrict__ rate, const uin
 // returns the first index with partial sum > r.  Same rule as k_select; the partial sums are associated
 // differently (ulp-level), so the index can differ from the sequential order only when r falls within rounding of
 // a partial sum.  Used by kmc_select for n > 65536 (or on request).
-__global__ void __launch_bounds__(1024) k_select_block_sums(const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, int chunk,
+static __global__ void __launch_bounds__(1024) k_select_block_sums(const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, int chunk,
                                                             double* __restrict__ bsum, int* __restrict__ bcount) {
     __shared__ double s_red[32];
     __shared__ int s_cnt[32];
@@ -575,7 +516,7 @@ __global__ void __launch_bounds__(1024) k_select_block_sums(const double* __rest
     }
 }
 
-__global__ void __launch_bounds__(1024) k_select_final(DevParams P, const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, int chunk,
+static __global__ void __launch_bounds__(1024) k_select_final(DevParams P, const double* __restrict__ rate, const uint8_t* __restrict__ surf, int n, int chunk,
                                                        int nblocks, const double* __restrict__ bsum, const int* __restrict__ bcount, double u,
                                                        long long* __restrict__ result, double* __restrict__ rtot) {
     __shared__ double s_seg[1024];
@@ -645,13 +586,13 @@ __global__ void __launch_bounds__(1024) k_select_final(DevParams P, const double
 // =============================================================================== misc
 
 // Periodic.py:22-25
-__global__ void k_put_all_in_box(DevParams P, double2* __restrict__ xy, int n) {
+static __global__ void k_put_all_in_box(DevParams P, double2* __restrict__ xy, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) xy[i].x = put_in_box(xy[i].x, P.L, P.halfL);
 }
 
 // Periodic.py:54-62
-__global__ void k_distances(DevParams P, const double2* __restrict__ a, int na, const double2* __restrict__ b, int nb,
+static __global__ void k_distances(DevParams P, const double2* __restrict__ a, int na, const double2* __restrict__ b, int nb,
                             double* __restrict__ out) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)na * nb) return;
@@ -660,7 +601,7 @@ __global__ void k_distances(DevParams P, const double2* __restrict__ a, int na, 
 }
 
 // Periodic.py:27-36
-__global__ void k_displacement(DevParams P, const double2* __restrict__ ri, const double2* __restrict__ rj, int k,
+static __global__ void k_displacement(DevParams P, const double2* __restrict__ ri, const double2* __restrict__ rj, int k,
                                double2* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
@@ -668,7 +609,7 @@ __global__ void k_displacement(DevParams P, const double2* __restrict__ ri, cons
 }
 
 // Bins.py:72-84: stencil populations of nq query points
-__global__ void k_nearby_count(DevParams P, CellView cv, const double2* __restrict__ q, int nq, long long* __restrict__ counts) {
+static __global__ void k_nearby_count(DevParams P, CellView cv, const double2* __restrict__ q, int nq, long long* __restrict__ counts) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     counts[i + 1] = stencil_population(P, cv, make_stencil(P, q[i].x, q[i].y));
@@ -676,7 +617,7 @@ __global__ void k_nearby_count(DevParams P, CellView cv, const double2* __restri
 }
 
 // in-place inclusive scan of a[1..m] (a[0] = 0), single block (list lengths, not a hot path)
-__global__ void k_scan_i64(long long* __restrict__ a, int m) {
+static __global__ void k_scan_i64(long long* __restrict__ a, int m) {
     __shared__ long long s_tot[1024];
     const int per = (m + blockDim.x - 1) / blockDim.x;
     const int lo = 1 + threadIdx.x * per, hi = min(lo + per, m + 1);
@@ -694,7 +635,7 @@ __global__ void k_scan_i64(long long* __restrict__ a, int m) {
     for (int i = lo; i < hi; ++i) { run += a[i]; a[i] = run; }
 }
 
-__global__ void k_nearby_fill(DevParams P, CellView cv, const double2* __restrict__ q, int nq,
+static __global__ void k_nearby_fill(DevParams P, CellView cv, const double2* __restrict__ q, int nq,
                               const long long* __restrict__ offs, long long cap, double2* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
@@ -707,7 +648,7 @@ __global__ void k_nearby_fill(DevParams P, CellView cv, const double2* __restric
 }
 
 // Bins.py:86-111 position lists, reference order; which: 0 adatom bonds, 1 substrate bonds
-__global__ void k_neighbor_fill(DevParams P, const double2* __restrict__ xy, int n, CellView cv, double bond,
+static __global__ void k_neighbor_fill(DevParams P, const double2* __restrict__ xy, int n, CellView cv, double bond,
                                 const long long* __restrict__ offs, long long cap, double2* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -723,14 +664,14 @@ __global__ void k_neighbor_fill(DevParams P, const double2* __restrict__ xy, int
     });
 }
 
-__global__ void k_i32_to_offsets(const int* __restrict__ counts, int n, long long* __restrict__ offs) {
+static __global__ void k_i32_to_offsets(const int* __restrict__ counts, int n, long long* __restrict__ offs) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) offs[i + 1] = counts[i];
     if (i == 0) offs[0] = 0;
 }
 
 // 2DGrowth.py:121,152: cand[a][i] = x[i] + a*s[i]/20/scale (same operation order: ((a*s)/20)/scale)
-__global__ void k_make_candidates(const double* __restrict__ x, const double* __restrict__ s, int n2, int K, double scale,
+static __global__ void k_make_candidates(const double* __restrict__ x, const double* __restrict__ s, int n2, int K, double scale,
                                   double* __restrict__ cand) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = blockIdx.y;
@@ -746,7 +687,7 @@ struct RelaxCtrl {
 };
 
 // first argmin of K energies (ys.index(min(ys)), 2DGrowth.py:123,155)
-__global__ void k_argmin(const double* __restrict__ e, int K, RelaxCtrl* __restrict__ ctrl) {
+static __global__ void k_argmin(const double* __restrict__ e, int K, RelaxCtrl* __restrict__ ctrl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int am = 0;
         double em = e[0];
@@ -758,7 +699,7 @@ __global__ void k_argmin(const double* __restrict__ e, int K, RelaxCtrl* __restr
 
 // after the forces at xnp = cand[amin]: maxF = max_i |F_i|^2 (:129,160), miny (:137), top = xnp.(xnp-xn),
 // bot = xn.xn (:143-144).  Also copies xnp out of the candidate batch.  Single block (deterministic).
-__global__ void k_relax_reduce(const double* __restrict__ cand, const double* __restrict__ xn, const double2* __restrict__ F,
+static __global__ void k_relax_reduce(const double* __restrict__ cand, const double* __restrict__ xn, const double2* __restrict__ F,
                                int n, RelaxCtrl* __restrict__ ctrl, double* __restrict__ xnp) {
     __shared__ double s_red[32];
     const double* xc = cand + (size_t)ctrl->amin * 2 * n;
@@ -782,7 +723,7 @@ __global__ void k_relax_reduce(const double* __restrict__ cand, const double* __
 }
 
 // snp = dxnp + beta*sn ; xn = xnp ; sn = snp  (2DGrowth.py:147-150)
-__global__ void k_cg_update(const double* __restrict__ F, double beta, double* __restrict__ sn, double* __restrict__ xn,
+static __global__ void k_cg_update(const double* __restrict__ F, double beta, double* __restrict__ sn, double* __restrict__ xn,
                             const double* __restrict__ xnp, int n2) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n2) return;
@@ -790,7 +731,7 @@ __global__ void k_cg_update(const double* __restrict__ F, double beta, double* _
     xn[i] = xnp[i];
 }
 
-__global__ void k_min_y(const double2* __restrict__ xy, int n, int want_max, double* __restrict__ out) {
+static __global__ void k_min_y(const double2* __restrict__ xy, int n, int want_max, double* __restrict__ out) {
     __shared__ double s_red[32];
     double v = want_max ? -INFINITY : INFINITY;
     for (int i = threadIdx.x; i < n; i += blockDim.x) v = want_max ? fmax(v, xy[i].y) : fmin(v, xy[i].y);

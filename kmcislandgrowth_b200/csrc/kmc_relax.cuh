@@ -54,7 +54,8 @@ struct RelaxArgs {
     unsigned long long* phase_ns;   // [8] block 0's time per phase (diagnostics)
 };
 
-// grid-wide barrier on a monotonically increasing counter (all blocks are co-resident: cooperative launch)
+// grid-wide barrier on a monotonically increasing 32-bit counter (all blocks are co-resident: cooperative launch);
+// arrival counts are compared modulo 2^32, so the counter may wrap in a very long relaxation
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -65,7 +66,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
         unsigned int v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while (v < target);
+        } while ((int)(v - target) < 0);          // wrap-safe: the counter only ever runs a few arrivals ahead of the target
     }
     ++epoch;
     __syncthreads();
@@ -202,7 +203,7 @@ struct RelaxSmem {
 };
 
 template <int G>
-__global__ void __launch_bounds__(256, 2) k_relax_persistent(RelaxArgs R) {
+static __global__ void __launch_bounds__(256, 2) k_relax_persistent(RelaxArgs R) {
     __shared__ RelaxSmem S;
     unsigned int epoch = 0;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;

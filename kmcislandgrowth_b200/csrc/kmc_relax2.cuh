@@ -53,10 +53,14 @@ struct WorkItem {
     int n2;                // length of the third partner range
 };
 
+constexpr int R2_MAXBLK = 160;      // grids have at most this many blocks (the control step keeps 5 partials per lane)
+
 struct Relax2Args {
     DevParams P;
     CellView sub;
-    int n, ncell2;
+    int n, ncell2;          // n: adatoms (an upper bound when n_dev is set)
+    const int* n_dev;       // optional: the adatom count lives in device memory (on-device event path, kmc_event.cu)
+    const int* status_dev;  // optional: the kernel does nothing when *status_dev != 0 (the placement before it failed)
     double2* x0;            // original order: input and output of the relaxation
     double2* pos[2];        // sorted: base iterate / candidate winner (ping-pong)
     double2* sdir[2];       // sorted: search direction (ping-pong across rebuilds)
@@ -204,12 +208,12 @@ __device__ __forceinline__ Ranges partner_ranges(const DevParams& P, const int* 
 // ---- rebuild of the sorted state from `n` source elements (7 barriers) ---------------------------
 // src_s / src_oidx may be null (direction 0 / identity index).
 __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double2* src_pos, const double2* src_s, const int* src_oidx,
-                                               double2* dst_pos, double2* dst_s, int* dst_oidx, unsigned int& epoch, Relax2Smem& S) {
+                                               double2* dst_pos, double2* dst_s, int* dst_oidx, unsigned int& epoch, Relax2Smem& S, int nA) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const DevParams& P = R.P;
     for (int c = gtid; c < R.ncell2; c += gthreads) R.start[c] = 0;
     relax2_barrier(R, epoch);
-    for (int k = gtid; k < R.n; k += gthreads) {
+    for (int k = gtid; k < nA; k += gthreads) {
         int nx, ny;
         bin_index(P, src_pos[k].x, src_pos[k].y, nx, ny);
         const int c = flat_cell(P, nx, ny);
@@ -238,7 +242,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         for (int i = t; i < R.ncell2; i += T) R.cursor[i] = R.start[i];
     }
     relax2_barrier(R, epoch);
-    for (int k = gtid; k < R.n; k += gthreads) {
+    for (int k = gtid; k < nA; k += gthreads) {
         const int slot = atomicAdd(&R.cursor[R.key[k]], 1);
         R.perm[slot] = k;
     }
@@ -513,7 +517,7 @@ __device__ __forceinline__ void relax2_items(const Relax2Args& R, const WorkItem
 
 // ---- F: one (mover, candidate) by one warp; sorted-state version of line_fix_one ------------------
 __device__ __forceinline__ double relax2_fix_one(const Relax2Args& R, const double2* pos, const double2* sdir, const int* oidx,
-                                                 double scale, int r, int a, int lane) {
+                                                 double scale, int r, int a, int lane, int nA) {
     const DevParams& P = R.P;
     const int nm = *R.n_movers;
     const int m = R.movers[r];
@@ -524,7 +528,7 @@ __device__ __forceinline__ double relax2_fix_one(const Relax2Args& R, const doub
     const bool in_grid = rx >= 0 && rx < P.nbx && ry >= 0 && ry < P.nby;
     const Stencil st = make_stencil(P, pm.x, pm.y);
     CellView ad;
-    ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = R.n;
+    ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = nA;
     double e = 0.0;
     if (P.aa_mode != 0) {
         // the partners' candidate positions only enter the pair distance: formed with one FMA (a few 1e-16 relative
@@ -703,7 +707,7 @@ __device__ __forceinline__ void relax2_item_range(const Relax2Args& R, int n_ite
 // Slot range covered by the stencils of this block's chunk of atoms.  The atoms are cell-sorted column-major and only
 // a few cells of a column are occupied, so the stencils of a contiguous chunk cover ONE contiguous slot range (three
 // adjacent columns) except at the periodic seam.  Valid until the next rebuild.
-__device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Smem& S, int& smin, int& smax, ERange& er) {
+__device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Smem& S, int& smin, int& smax, ERange& er, int nA) {
     const int T = blockDim.x;
     {   // the block's work items: a contiguous range of the (home-cell ordered) list, dealt to its warps round robin; the
         // first R2_WI of every warp are cached.  Contiguous items = adjacent home cells = ONE contiguous slot range of
@@ -738,12 +742,12 @@ __device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Sm
         for (int i = er.submin + threadIdx.x; i < er.submax; i += T) S.esub[i - er.submin] = R.sub.sxy[i];      // static: loaded once
     }
     {   // stencil ranges of this block's atoms
-        const int per = (R.n + gridDim.x - 1) / gridDim.x;
-        const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+        const int per = (nA + gridDim.x - 1) / gridDim.x;
+        const int lo = blockIdx.x * per, hi = min(lo + per, nA);
         for (int i = threadIdx.x; i < 4 * min(hi - lo, R2_NBRC); i += T) S.nbrc[i >> 2][i & 3] = R.nbr[4 * lo + i];
     }
-    const int per = (R.n + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+    const int per = (nA + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(lo + per, nA);
     __syncthreads();
     if (threadIdx.x == 0) { S.smin = 0x7fffffff; S.smax = -1; }
     __syncthreads();
@@ -758,7 +762,7 @@ __device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Sm
             if (ae.w > ab.w) { mn = min(mn, ab.w); mx = max(mx, ae.w); }
             if (mx > mn) { atomicMin(&S.smin, mn); atomicMax(&S.smax, mx); }
         }
-    } else if (threadIdx.x == 0 && hi > lo) { S.smin = 0; S.smax = R.n; }
+    } else if (threadIdx.x == 0 && hi > lo) { S.smin = 0; S.smax = nA; }
     __syncthreads();
     smin = S.smin; smax = S.smax;
     if (!(smax > smin && (smax - smin) <= R2_STAGE)) { smin = 0; smax = 0; }
@@ -773,7 +777,7 @@ __device__ __forceinline__ double group_sum_rt(double v, int G) {
 // The chunk is processed in ONE pass with T/atoms lanes per atom (see below); larger chunks take several passes.
 __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2* pos, double2* sdir, const int* oidx, int mode, double beta,
                                               double scale, bool count_pairs, Relax2Smem& S, unsigned int& parity, int smin, int smax,
-                                              bool issue_here, unsigned long long* tm = nullptr) {
+                                              bool issue_here, int nA, unsigned long long* tm = nullptr) {
 #define GMARK(k)                                                                          \
     if (tm && threadIdx.x == 0 && blockIdx.x == R.phase_block) {                          \
         const unsigned long long _t = gtimer();                                           \
@@ -782,10 +786,10 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
     }
     const DevParams& P = R.P;
     const int T = blockDim.x;
-    const int per = (R.n + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+    const int per = (nA + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(lo + per, nA);
     CellView ad;
-    ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = R.n;
+    ad.start = R.start; ad.sxy = pos; ad.sidx = oidx; ad.n = nA;
     double mf = 0.0;
     unsigned long long visits = 0;
     // The neighbourhood of this block's atoms [smin, smax) was determined after the last rebuild (relax2_stage_range);
@@ -824,7 +828,7 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
             pi = (staged && slot >= smin && slot < smax) ? npos[slot] : pos[slot];
             if (ab.x >= 0) {        // stencil ranges cached at the last rebuild
                 if (P.aa_mode == 0) {
-                    for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, npos[s], P.E_a, P.ra2, ax, ay);
+                    for (int s = lane; s < nA; s += G) acc_force(P, pi.x, pi.y, npos[s], P.E_a, P.ra2, ax, ay);
                 } else {
                     flat_forces(P, npos, ab, ae, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
                 }
@@ -834,7 +838,7 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
             } else {                // atoms outside the grid / y-wrapped stencils: generic walk from the raw position
                 const Stencil st = make_stencil(P, pi.x, pi.y);
                 if (P.aa_mode == 0) {
-                    for (int s = lane; s < R.n; s += G) acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
+                    for (int s = lane; s < nA; s += G) acc_force(P, pi.x, pi.y, pos[s], P.E_a, P.ra2, ax, ay);
                 } else {
                     stencil_forces(P, ad, st, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
                 }
@@ -890,9 +894,12 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
         t_mark = _t;                                               \
     }
 
-__global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
+static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     extern __shared__ __align__(16) unsigned char r2_smem_raw[];
     Relax2Smem& S = *reinterpret_cast<Relax2Smem*>(r2_smem_raw);
+    if (R.status_dev && *R.status_dev != 0) return;            // the placement of this event failed: nothing to relax (uniform exit)
+    const int nA = R.n_dev ? *R.n_dev : R.n;                   // adatoms of this relaxation
+    if (nA <= 0) return;
     unsigned int epoch = 0;
     unsigned int tma_parity = 0;
     int st_min = 0, st_max = 0;      // staged slot range of this block (relax2_stage_range)
@@ -958,8 +965,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         }
         if (blockIdx.x == 0) {          // ordered list of mover slots
             const int T = blockDim.x, t = threadIdx.x;
-            const int per = (R.n + T - 1) / T;
-            const int lo = t * per, hi = min(lo + per, R.n);
+            const int per = (nA + T - 1) / T;
+            const int lo = t * per, hi = min(lo + per, nA);
             int cnt = 0;
             for (int i = lo; i < hi; ++i) cnt += R.flag[i];
             S.u.e.scan[t] = cnt;
@@ -980,7 +987,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             const int nm0 = S.u.e.scan[T - 1];
             if (nblk > 1 && nm0 > 0 && nm0 <= R2_FIX_INLINE)
                 for (int w = warp; w < nm0 * KC; w += R2_THREADS / 32) {
-                    const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane);
+                    const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane, nA);
                     if (lane == 0) R.fix[w] = e;
                 }
         }
@@ -1007,11 +1014,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             if (R.debug != 2) relax2_items(R, S.wit[warp], er.kb + warp, wpb, er.ke, O, inv_step, lane, acc, eslow);
         }
         if (P.aa_mode == 0) {
-            for (int i = gwarp; i < R.n; i += nwarps) {
+            for (int i = gwarp; i < nA; i += nwarps) {
                 const double2 pi = pos[i], si = sdir[i];
-                for (int j0 = i + 1; j0 < R.n; j0 += 32) {
+                for (int j0 = i + 1; j0 < nA; j0 += 32) {
                     const int j = j0 + lane;
-                    const bool valid = j < R.n;
+                    const bool valid = j < nA;
                     double dx0 = 0.0, dy0 = 0.0, ddx = 0.0, ddy = 0.0;
                     if (valid) {
                         const double2 pj = pos[j], sj = sdir[j];
@@ -1064,8 +1071,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         // everything the S phase needs is requested here, in one L2 round trip: the mover count, this thread's atom
         // (the block's chunk of slots, as in the force phase) and this warp's share of the partial sums
         const int nm = *R.n_movers;
-        const int per = (R.n + nblk - 1) / nblk;
-        const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+        const int per = (nA + nblk - 1) / nblk;
+        const int lo = blockIdx.x * per, hi = min(lo + per, nA);
         const int myslot = lo + threadIdx.x;
         double2 pre_p = make_double2(0, 0), pre_s = make_double2(0, 0);
         unsigned int pre_f = 0;
@@ -1083,7 +1090,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         mover_sum += nm;
         if (nm > (nblk > 1 ? R2_FIX_INLINE : 0)) {
             for (int w = gwarp; w < nm * KC; w += nwarps) {
-                const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane);
+                const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane, nA);
                 if (lane == 0) R.fix[w] = e;
             }
             relax2_barrier(R, epoch);
@@ -1184,19 +1191,19 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         bool issue_here = false;
         if (rebuild_now) {
             issue_here = true;
-            relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S);
+            relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S, nA);
             if (gtid == 0) *R.need_rebuild = 0;
             if (*R.n_items > R.item_cap) overflow = true;
             ++rebuilds;
             layout_x0 = false;
-            relax2_stage_range(R, S, st_min, st_max, er);
+            relax2_stage_range(R, S, st_min, st_max, er, nA);
             n_items_reg = *R.n_items;
             PHASE2_MARK(7)
             cs ^= 1;          // the rebuilt x_np now lives in pos[cur]: make it the "next" buffer by flipping cur
             cur ^= 1;
         }
         PHASE2_MARK(11)
-        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, tma_parity, st_min, st_max, issue_here, &t_mark);
+        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, tma_parity, st_min, st_max, issue_here, nA, &t_mark);
         PHASE2_MARK(5)
         if (R.debug == 8 && threadIdx.x == 0) R.blk_ns[2 * blockIdx.x + 1] += gtimer() - t_blk;
         relax2_barrier(R, epoch);
@@ -1211,8 +1218,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     for (;;) {                                                         // one pass == one (recursive) call of Relaxation
         if (scale > 1024) { scale = 16; threshold *= 10; }              // :111-113
         e_fresh = false;                                                // the pass rewrites positions, directions and flags
-        const int per = (R.n + nblk - 1) / nblk;
-        const int lo = blockIdx.x * per, hi = min(lo + per, R.n);
+        const int per = (nA + nblk - 1) / nblk;
+        const int lo = blockIdx.x * per, hi = min(lo + per, nA);
         if (layout_x0) {
             // restart from the ORIGINAL positions while the sorted layout is still the one built from them: the cell list,
             // the work items and the first direction dx0 = F(x0) are unchanged (only the mover flags depend on the new
@@ -1228,11 +1235,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 R.flag[slot] = mover_flag(P, p, s0, (double)scale);
             }
         } else {
-            relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S);
+            relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S, nA);
             if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
-            relax2_stage_range(R, S, st_min, st_max, er);
+            relax2_stage_range(R, S, st_min, st_max, er, nA);
             n_items_reg = *R.n_items;
-            relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true);   // dx0, sn = dx0  :120,125
+            relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true, nA);   // dx0, sn = dx0  :120,125
             first_pass = false;
             __syncthreads();
             for (int slot = lo + threadIdx.x; slot < hi; slot += R2_THREADS) R.sdir[cs ^ 1][slot] = R.sdir[cs][slot];     // dx0, kept for the restarts
@@ -1259,7 +1266,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     if (status != -4) {
         const double2* posn = R.pos[cur ^ 1];
         const int* oidx = R.oidx[cs];
-        for (int slot = gtid; slot < R.n; slot += gthreads) {
+        for (int slot = gtid; slot < nA; slot += gthreads) {
             double2 p = posn[slot];
             p.x = put_in_box(p.x, P.L, P.halfL);
             R.x0[oidx[slot]] = p;

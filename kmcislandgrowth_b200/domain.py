@@ -122,6 +122,10 @@ class DomainSweeps(object):
     """Force / energy / rate sweeps of one configuration spread over the ranks of a process group."""
 
     def __init__(self, gv, substrate, adatoms, rank, world, backend_factory, dist=None, device=None):
+        if int(getattr(gv, "aa_mode", 0)) != 1:
+            # all-pairs adatom sums (aa_mode 0, Energy.py:62-67) need every adatom on every rank: a one-column halo would
+            # silently drop pairs.  The decomposition is defined for the stencil mode only (SURVEY.md 8e).
+            raise ValueError("domain decomposition needs aa_mode == 1 (bins3x3 adatom sums); got aa_mode=%r" % getattr(gv, "aa_mode", 0))
         self.gv, self.rank, self.world, self.dist, self.device = gv, rank, world, dist, device
         self.dec = Decomposition(gv, world)
         # static substrate: own columns + halo columns

@@ -359,6 +359,41 @@ class Context(object):
     def hop_place(self, sbins, k, u):
         check(self.lib.kmc_hop_place(self.handle, sbins.handle, int(k), float(u)))
 
+    def fp64_peak(self, repeats=5):
+        """measured non-tensor FP64 FMA rate of the device -> (TFLOP/s, ms of the best run)"""
+        tf, ms = C.c_double(0), C.c_double(0)
+        check(self.lib.kmc_fp64_peak(self.handle, int(repeats), C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
+
+    def relax_diag(self):
+        """counters of the last relaxation: dict(resorts, movers, work_items)"""
+        out = (C.c_int64 * 4)()
+        check(self.lib.kmc_relax_diag(self.handle, out))
+        return {"resorts": int(out[0]), "movers": int(out[1]), "work_items": int(out[2])}
+
+    def set_event_mode(self, mode):
+        """1 (default): a KMC event is queued as one chain of kernels with a single host synchronisation;
+        0: first-generation host-stepped placement (same results, cross-check)"""
+        check(self.lib.kmc_set_event_mode(self.handle, int(mode)))
+
+    def event_enqueue(self, sbins, u0, u1, max_line_searches=0):
+        """queue one KMC event on the context's stream; event_finish() waits for it and returns its outcome"""
+        check(self.lib.kmc_event_enqueue(self.handle, sbins.handle, float(u0), float(u1), int(max_line_searches)))
+
+    def event_ready(self):
+        """True when the enqueued event has completed on the device (event_finish will not block)"""
+        rc = self.lib.kmc_event_ready(self.handle)
+        if rc < 0:
+            check(rc)
+        return rc == 1
+
+    def event_finish(self):
+        kind, hk, rtot, st = C.c_int32(-1), C.c_int64(-1), C.c_double(0), KmcRelaxStats()
+        rc = self.lib.kmc_event_finish(self.handle, C.byref(kind), C.byref(hk), C.byref(rtot), C.byref(st))
+        if rc != 0 and rc != _lib.KMC_E_ITERCAP:
+            check(rc)
+        return kind.value, hk.value, rtot.value, st
+
     def event(self, sbins, u0, u1, max_line_searches=0):
         """one KMC event -> (kind 0 deposit / 1 hop, hop_k, Rtot, stats)"""
         kind, hk, rtot, st = C.c_int32(-1), C.c_int64(-1), C.c_double(0), KmcRelaxStats()
@@ -367,6 +402,25 @@ class Context(object):
         if rc != 0 and rc != _lib.KMC_E_ITERCAP:
             check(rc)
         return kind.value, hk.value, rtot.value, st
+
+
+def events_batch(ctxs, sbins, u0, u1, max_line_searches=0):
+    """One KMC event of each of R replicas (one Context + substrate cell list each, all on the same device or not):
+    every event is queued before the first is waited for (kmc_events_batch).  -> list of (kind, hop_k, Rtot, stats, rc)"""
+    R = len(ctxs)
+    if R == 0:
+        return []
+    lib = ctxs[0].lib
+    hc = (C.c_void_p * R)(*[c.handle for c in ctxs])
+    hb = (C.c_void_p * R)(*[b.handle for b in sbins])
+    a0 = (C.c_double * R)(*[float(v) for v in u0])
+    a1 = (C.c_double * R)(*[float(v) for v in u1])
+    kinds, hks, rtots = (C.c_int32 * R)(), (C.c_int64 * R)(), (C.c_double * R)()
+    stats, rcs = (KmcRelaxStats * R)(), (C.c_int32 * R)()
+    rc = lib.kmc_events_batch(hc, hb, R, a0, a1, int(max_line_searches), kinds, hks, rtots, stats, rcs)
+    if rc != 0:
+        check(rc)
+    return [(kinds[r], hks[r], rtots[r], stats[r], rcs[r]) for r in range(R)]
 
 
 def _count(a):

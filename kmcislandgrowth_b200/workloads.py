@@ -83,3 +83,26 @@ def make(name, **over):
     W, Hs, Ha, n, seed, aa = CONFIGS[name]
     gv = constants_for(W, Hs, Ha, aa_mode=aa, hop_index_mode=1 if aa else 0, deposit_mode=1 if aa else 0, **over)
     return gv, substrate(gv), film(gv, n, seed)
+
+
+# ---- the bench protocol of configs[1] (bench.py, tests/test_gpu_parity.py::test_headline_*) ---------------------------
+BENCH_SEED = 1234               # uniform stream of the bench trajectory
+BENCH_PRERELAX_CAP = 200000     # line-search bound of the untimed set-up relaxation (it converges long before)
+
+
+def bench_uniforms(n_events):
+    """the explicit uniform stream of the bench trajectory: u[s] = (selection, placement) of event s"""
+    return np.random.default_rng(BENCH_SEED).uniform(0, 1, (n_events, 2))
+
+
+def bench_prerelax(ctx, sbins, cap=BENCH_PRERELAX_CAP):
+    """untimed set-up: relax the synthetic film with the reference's own Relaxation (2DGrowth.py:97-166) to ITS convergence
+    criterion, so that the timed events start from a relaxed state; -> stats of the last relaxation, total line searches"""
+    total = 0
+    st = None
+    while total < cap:
+        st = ctx.relax(sbins, 16, 1e-4, min(20000, cap - total))
+        total += int(st.line_searches)
+        if int(st.status) == 0:
+            break
+    return st, total

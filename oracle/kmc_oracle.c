@@ -452,12 +452,19 @@ static int line_search(const OrcParams* p, const double* x, const double* s, int
 /* 2DGrowth.py:97-166.  Restarts (scale*2, or threshold*10 past scale 1024) start again from the
  * ORIGINAL positions handed to the call, exactly like the recursion in the reference. */
 int orc_relaxation(const OrcParams* p, double* x, int64_t n, const OrcBins* sbins, OrcRelaxStats* st, int64_t max_ls) {
+    return orc_relaxation_ex(p, x, n, sbins, st, max_ls, 16, 1e-4);       /* the defaults of 2DGrowth.py:97 */
+}
+
+/* Relaxation(adatoms, substrate_bins, scale, threshold) with explicit start values (LocalRelaxation calls it with
+ * scale=4, 2DGrowth.py:192,198) */
+int orc_relaxation_ex(const OrcParams* p, double* x, int64_t n, const OrcBins* sbins, OrcRelaxStats* st, int64_t max_ls,
+                      int scale0, double threshold0) {
     size_t bytes = sizeof(double) * 2 * (size_t)(n > 0 ? n : 1);
     double* x0 = (double*)malloc(bytes); double* xn = (double*)malloc(bytes); double* xnp = (double*)malloc(bytes);
     double* sn = (double*)malloc(bytes); double* snp = (double*)malloc(bytes); double* dxnp = (double*)malloc(bytes);
     double* tmp = (double*)malloc(bytes); double* cand = (double*)malloc(bytes);
     memcpy(x0, x, bytes);
-    int scale = 16; double threshold = 1e-4; int rc = 0;
+    int scale = scale0; double threshold = threshold0; int rc = 0;
     OrcRelaxStats local; memset(&local, 0, sizeof(local));
     if (!st) st = &local; else memset(st, 0, sizeof(*st));
     int64_t pairs_e = (n > 0) ? count_pairs_energy(p, x, n, sbins) : 0;

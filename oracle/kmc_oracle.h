@@ -91,6 +91,8 @@ int64_t orc_select(const OrcParams* p, const double* rate_dense, int64_t n, doub
 typedef struct OrcRelaxStats { int64_t line_searches; int64_t restarts; int64_t pair_evals; double maxF; int32_t final_scale; double final_threshold; } OrcRelaxStats;
 /* :97-166. x is relaxed in place. returns 0 ok, <0 on iteration cap */
 int  orc_relaxation(const OrcParams* p, double* x, int64_t n, const OrcBins* sbins, OrcRelaxStats* st, int64_t max_line_searches);
+int  orc_relaxation_ex(const OrcParams* p, double* x, int64_t n, const OrcBins* sbins, OrcRelaxStats* st, int64_t max_line_searches,
+                       int scale0, double threshold0);
 /* :64-95 without the trailing Relaxation: appends the new atom to ad (capacity n+1). */
 int  orc_deposit_place(const OrcParams* p, double* ad, int64_t n, const OrcBins* sbins, double u);
 /* :229-255 without the trailing Relaxation: removes atom k and appends it at the chosen site. */

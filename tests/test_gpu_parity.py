@@ -688,3 +688,136 @@ def test_edge_cases():
         assert abs(e1 - eo1) < 1e-11 * abs(eo1)
     finally:
         del Constants.aa_mode
+
+
+# ---- the headline configuration itself (BASELINE.json configs[1]: 256x256 substrate, 10 000 adatoms) ------------------
+def _bench_fixture(name="cfg2_256x256_10k"):
+    return json.load(open(os.path.join(GOLDEN, "bench_%s.json" % name)))
+
+
+def test_headline_events_follow_the_oracle_uncapped():
+    """The bench trajectory itself: from the bench's relaxed start state, the first events of the seeded stream are run
+    UNCAPPED on the GPU (kmc_event: one device-resident chain) and on the CPU oracle.  Same event kind and hop index, same
+    number of line searches and restarts in every relaxation (each argmin of each line search agrees, or the counts would
+    diverge), positions within 1e-7.  The events cover >= 300 line searches with restarts and re-sorts of the cell-sorted
+    state, and the oracle confirms the first entries of the fixture the reference arm of bench.py extrapolates with
+    (tests/golden/bench_cfg2_256x256_10k.json: recorded on the GPU)."""
+    from kmcislandgrowth_b200 import Growth, runtime, workloads
+    gv, sub, ad0 = workloads.make("cfg2_256x256_10k")
+    fx = _bench_fixture()
+    sim = Growth.Simulation(adatoms=ad0, substrate=sub, device=0, params=runtime.params_from(gv))
+    st, total = workloads.bench_prerelax(sim.ctx, sim.sbins)
+    assert int(st.status) == 0, "the set-up relaxation must converge (%d line searches)" % total
+    if "prerelax_line_searches" in fx:
+        assert total == fx["prerelax_line_searches"]
+    o = _oracle_for(gv)
+    orc.set_num_threads(os.cpu_count() or 1)
+    osb = o.PutInBins(sub)
+    us = workloads.bench_uniforms(8)
+    state = sim.adatoms
+    n_ls = n_restarts = n_resorts = 0
+    budget = int(os.environ.get("KMC_TEST_HEADLINE_LS", "1400"))      # CPU cost ~55 ms per line search on 16 cores
+    done = 0
+    for s in range(8):
+        if done >= 2 and n_ls + fx["line_searches"][s] > budget:
+            break
+        rec = sim.step(us[s, 0], us[s, 1], 0)
+        diag = sim.ctx.relax_diag()
+        want, kind, hk, rtot, ost, rc = o.Event(state, osb, us[s], 0)
+        assert rc == 0 and rec["status"] == 0
+        assert rec["kind"] == kind and rec["hop_k"] == hk, s
+        assert abs(rec["rtot"] - rtot) <= 1e-9 * abs(rtot)
+        assert rec["line_searches"] == int(ost.line_searches), (s, rec["line_searches"], int(ost.line_searches))
+        assert rec["restarts"] == int(ost.restarts), s
+        if "prerelax_line_searches" in fx:          # fixture of the current bench protocol (converged set-up relaxation)
+            assert rec["line_searches"] == fx["line_searches"][s] and rec["kind"] == fx["kinds"][s], "bench fixture entry %d is stale" % s
+        state = sim.adatoms
+        assert state.size == want.size
+        assert float(np.max(np.abs(state - want))) < 1e-7, s
+        n_ls += rec["line_searches"]
+        n_restarts += rec["restarts"]
+        n_resorts += diag["resorts"]
+        done += 1
+    assert done >= 2 and n_ls >= 300, (done, n_ls)
+    assert n_restarts >= 1 and n_resorts >= 1, (n_restarts, n_resorts)
+    sim.close()
+
+
+def test_event_modes_agree():
+    """device-resident event chain (default) == host-stepped placement (first generation), bit for bit, on hops and deposits"""
+    from kmcislandgrowth_b200 import Growth, runtime, workloads
+    for W, Hs, Ha, n, aa in [(18, 10, 10, 30, 0), (64, 16, 16, 900, 1)]:
+        gv = workloads.constants_for(W, Hs, Ha, aa_mode=aa, hop_index_mode=1 if aa else 0, deposit_mode=1 if aa else 0)
+        sub = workloads.substrate(gv)
+        ad = workloads.film(gv, n, 5)
+        us = np.random.default_rng(77).uniform(0, 1, (10, 2))
+        us[3, 0] = 0.999999999           # force deposits as well (the film's hop rates dwarf Rd)
+        us[7, 0] = 1.0 - 2 ** -53
+        outs = []
+        for mode in (1, 0):
+            sim = Growth.Simulation(adatoms=ad, substrate=sub, device=0, params=runtime.params_from(gv))
+            sim.set_modes(event_mode=mode)
+            recs = [sim.step(us[s, 0], us[s, 1], 40) for s in range(10)]
+            outs.append((recs, sim.adatoms))
+            sim.close()
+        for a, b in zip(outs[0][0], outs[1][0]):
+            assert (a["kind"], a["hop_k"], a["line_searches"], a["restarts"]) == (b["kind"], b["hop_k"], b["line_searches"], b["restarts"])
+            assert a["rtot"] == b["rtot"]
+        assert np.array_equal(outs[0][1], outs[1][1])
+        assert {r["kind"] for r in outs[0][0]} == {0, 1}, "the event mix must cover hops and deposits"
+
+
+def test_batched_replicas_equal_sequential_runs():
+    """kmc_events_batch (configs[3]): R replicas with their own constants and uniform streams advanced together give
+    exactly the trajectories of R sequential simulations"""
+    from kmcislandgrowth_b200 import Growth, replicas, runtime
+    grid = replicas.sweep_grid(2, 3)
+    n_events = 12
+    seq = []
+    for r in range(len(grid)):
+        gv = replicas.replica_constants(r, grid)
+        sim = Growth.Simulation(adatoms=None, substrate=replicas.workloads.substrate(gv), device=0, params=runtime.params_from(gv))
+        us = np.random.default_rng(1000 + r).uniform(0, 1, (n_events, 2))
+        recs = [sim.step(us[t, 0], us[t, 1], 0) for t in range(n_events)]
+        seq.append(([(x["kind"], x["hop_k"], x["line_searches"]) for x in recs], sim.adatoms))
+        sim.close()
+    batch = replicas.ReplicaBatch(list(range(len(grid))), grid, device=0)
+    out = batch.run(n_events)
+    for r in range(len(grid)):
+        assert out["log"][r] == seq[r][0]
+        assert np.array_equal(out["adatoms"][r], seq[r][1])
+    batch.close()
+
+
+def test_local_relaxation_matches_reference_semantics():
+    """Growth.LocalRelaxation (2DGrowth.py:168-199): stencil atoms relaxed on their own (scale 4), then a global
+    relaxation when max|F|^2 > 1e-3 -- against the same composition on the oracle's primitives"""
+    from kmcislandgrowth_b200 import Bins, Growth, workloads
+    gv = workloads.constants_for(18)
+    o = _oracle_for(gv)
+    sub = Growth.InitSubstrate()
+    sb, osb = Bins.PutInBins(sub), o.PutInBins(sub)
+    rng = np.random.default_rng(3)
+    n = 14
+    ad = np.empty(2 * n)
+    ad[0::2] = (np.arange(n) % 9) * 2.7 - 12.0 + rng.normal(0, 0.05, n)
+    ad[1::2] = (np.arange(n) // 9 + 1) * 2.338 + rng.normal(0, 0.05, n)
+    around = ad[4:6].copy()
+    stats = []
+    got = Growth.LocalRelaxation(ad, sb, around, stats=stats)
+    # the same steps on the oracle
+    nearby = np.asarray(o.NearbyAtoms(around[0], around[1], o.PutInBins(ad)))
+    D = o.Distances(nearby, ad)
+    idx = sorted([int(np.nonzero(row == 0)[0][0]) for row in D], reverse=True)
+    rest, relaxing = ad.copy(), []
+    for i in idx:
+        relaxing += [rest[2 * i], rest[2 * i + 1]]
+        rest = np.delete(np.delete(rest, 2 * i), 2 * i)
+    x, st1, rc = o.Relaxation(np.array(relaxing), osb, scale=4)
+    allx = np.append(rest, x)
+    F = o.AdatomAdatomForces(allx) + o.AdatomSubstrateForces(allx, osb)
+    if float(np.max(F[0::2] ** 2 + F[1::2] ** 2)) > 1e-3:
+        allx, st2, rc = o.Relaxation(allx, osb, scale=4)
+        assert len(stats) == 2 and int(stats[1].line_searches) == int(st2.line_searches)
+    assert int(stats[0].line_searches) == int(st1.line_searches)
+    assert got.size == allx.size and float(np.max(np.abs(got - allx))) < 1e-6
