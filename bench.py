@@ -249,12 +249,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def progress(msg):
+        if rank == 0:
+            print("[bench %.1fs] %s" % (time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
+
+    t_start = time.perf_counter()
     sampler = ClockSampler(local)
     # untimed set-up: the synthetic film is relaxed to the reference's own convergence criterion (2DGrowth.py:131)
     t_pre = time.perf_counter()
     st, prerelax_ls = workloads.bench_prerelax(ctx, sim.sbins, args.prerelax)
     t_pre = time.perf_counter() - t_pre
+    progress("set-up relaxation: %d line searches, status %d" % (prerelax_ls, int(st.status)))
     fp64_peak_tflops, _ = ctx.fp64_peak(5)            # measured non-tensor FP64 FMA rate of this device
+    progress("fp64 peak %.1f TFLOP/s" % fp64_peak_tflops)
     nsteps = args.warmup + args.steps
     us = workloads.bench_uniforms(max(nsteps, 64))
     if args.record_fixture and rank == 0:
@@ -276,6 +283,7 @@ def run_ours(args):
         flush.zero_()
         sim.step(us[s, 0], us[s, 1], cap)
     sampler.sample()
+    progress("warm-up done")
 
     # ---- timed region 1: device-resident trajectory
     state0 = sim.adatoms.copy()           # both timed regions run the SAME events from this state
@@ -310,6 +318,7 @@ def run_ours(args):
         fam[f] = {"ms": ms, "launches": cnt}
     ctx.timing_reset()
 
+    progress("timed region 1 done: %.1f ms per event" % (t_dev / max(args.steps, 1) * 1e3))
     # ---- timed region 2: the same events through the host API (upload from pinned memory, event, read back)
     host = torch.from_numpy(state0.copy()).pin_memory()
     n_at = host.numel() // 2
@@ -330,6 +339,7 @@ def run_ours(args):
             host = torch.from_numpy(out.copy()).pin_memory()
     barrier()
     t_e2e = time.perf_counter() - t0
+    progress("timed region 2 done")
     clocks = sampler.summary()
 
     tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)

@@ -36,6 +36,7 @@ extern "C" {
 #define KMC_E_CAPACITY (-4)    /* output buffer too small                                     */
 #define KMC_E_NOCANDIDATE (-5) /* HopAtom found no surface atom within 3 r_a (reference: randint(0,-1) raises, 2DGrowth.py:248) */
 #define KMC_E_ITERCAP (-6)     /* relaxation hit the caller's line-search cap                 */
+#define KMC_E_TIMEOUT (-8)     /* a device-side wait of the persistent relaxation kernel timed out (watchdog) */
 #define KMC_E_DEPOSIT (-7)     /* deposition probe never came close to anything (2DGrowth.py:80-92 would loop forever) */
 
 /* Values of the reference's Constants.py (and the two literals of 2DGrowth.py), computed on the

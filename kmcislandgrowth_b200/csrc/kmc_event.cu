@@ -270,10 +270,14 @@ constexpr size_t MAIL_EVENT_OFFSET = 1024;         // EventMail's place in the p
 // queue the placement of an event on the stream.  force_kind -1: rate table + selection decide.
 int enqueue_placement(KmcCtx* c, const KmcBins* sb, double u0, double u1, int force_kind, int who_override, bool need_surf) {
     const int n = (int)c->st_n;
+    double tq = kmc_now();
+#define ENQ_MARK(i) { const double _t = kmc_now(); c->enq_s[i] += _t - tq; tq = _t; }
     TRY(kmc_state_reserve(c, n + 1));
     EventMail* mail;
     TRY(slot(c, S_EVMAIL, 1, &mail));
+    ENQ_MARK(4)
     LAUNCH(c, "event_init", k_ev_init, 1, 1, mail, c->st_n_dev, n);
+    ENQ_MARK(5)
     double* rate = nullptr;
     uint8_t* surf = nullptr;
     CellView ad;
@@ -289,7 +293,9 @@ int enqueue_placement(KmcCtx* c, const KmcBins* sb, double u0, double u1, int fo
             TRY(kmc_scratch_cells(c, (const double2*)c->st_xy, n, 1, &ad));
         }
     }
+    ENQ_MARK(6)
     if (force_kind < 0) TRY(kmc_select_dev(c, rate, surf, n, u0, mail->res, &mail->rtot, nullptr));      // :319-324
+    ENQ_MARK(7)
     EvArgs A{};
     A.P = c->dp; A.ad = ad; A.sub = view_of(sb);
     A.xy = (double2*)c->st_xy;
@@ -305,14 +311,21 @@ int enqueue_placement(KmcCtx* c, const KmcBins* sb, double u0, double u1, int fo
         A.hex_dx[i] = std::cos(t) * c->hp.r_a;
         A.hex_dy[i] = std::sin(t) * c->hp.r_a;
     }
+    ENQ_MARK(8)
     if (force_kind != 1) LAUNCH(c, "event_deposit", k_ev_deposit, 1, EV_THREADS, A);
+    ENQ_MARK(9)
     if (force_kind != 0 && n > 0) {
         LAUNCH(c, "event_hop", k_ev_hop, 1, EV_THREADS, A);
         LAUNCH(c, "event_apply", k_ev_apply, cdiv(n, 256), 256, A);
         LAUNCH(c, "event_apply", k_ev_copyback, cdiv(n, 256), 256, A);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync((char*)c->h_mail + MAIL_EVENT_OFFSET, mail, sizeof(EventMail), cudaMemcpyDeviceToHost, c->stream));
+    ENQ_MARK(10)
+    static_assert(sizeof(EventMail) % 4 == 0, "EventMail is copied word by word");
+    TRY(kmc_to_mailbox_async(c, MAIL_EVENT_OFFSET, mail, sizeof(EventMail)));
+    CK(cudaGetLastError());
+    ENQ_MARK(11)
+#undef ENQ_MARK
     return 0;
 }
 
@@ -347,10 +360,14 @@ int kmc_event_enqueue(KmcCtx* c, const KmcBins* sb, double u0, double u1, int64_
     if (c->ev_pending) return kmc_fail(KMC_E_ARG, "kmc_event_enqueue: the previous event of this context was not finished");
     DevGuard guard(c);
     const int n = (int)c->st_n;
+    const double t0 = kmc_now();
     TRY(enqueue_placement(c, sb, u0, u1, -1, -1, false));
+    const double t1 = kmc_now();
     EventMail* mail = (EventMail*)c->slots[S_EVMAIL].p;
     if (c->relax_mode == 2)       // :94 / :256 -- the relaxation reads the adatom count and the placement status on the device
         TRY(kmc_relax2_enqueue(c, sb, 16, 1e-4, max_ls, n + 1, c->st_n_dev, &mail->status));
+    c->enq_s[0] += t1 - t0;
+    c->enq_s[1] += kmc_now() - t1;
     c->ev_pending = true;
     c->ev_max_ls = max_ls;
     c->ev_sbins = sb;

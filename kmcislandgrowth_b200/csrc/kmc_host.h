@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -80,6 +81,7 @@ struct KmcCtx {
     std::vector<std::string> families;
     // pinned mailbox for small readbacks
     void* h_mail = nullptr;
+    void* h_mail_dev = nullptr;     // the same pinned page as seen from the device (mapped)
     // trajectory state
     double* st_xy = nullptr;
     int64_t st_n = 0, st_cap = 0;
@@ -102,6 +104,7 @@ struct KmcCtx {
     int select_mode = 0;            // 0: sequential-order sums up to 65536 atoms, block scan beyond; 1: always sequential; 2: always block scan
     int event_mode = 1;             // 1 (default): the whole event is enqueued without a host round trip; 0: host-stepped placement (cross-check)
     int sm_count = 148;
+    double enq_s[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // diagnostics (KMC_ENQ_TIMING): host seconds spent in the parts of kmc_event_enqueue
     int64_t diag[4] = {0, 0, 0, 0};  // counters of the last relaxation (kmc_relax_diag)
     // an event that was enqueued and not yet finished (kmc_event_enqueue / kmc_event_finish)
     bool ev_pending = false;
@@ -129,7 +132,7 @@ enum Slot {
     S_F, S_FAA, S_FAS, S_X0, S_XN, S_XNP, S_SN, S_TMP0, S_TMP1, S_TMP2, S_TMP3,
     S_FLAG, S_MOVERS, S_NMOV, S_LPART, S_FIX, S_AMIN, S_RED, S_SYNC,
     S_POS0, S_POS1, S_SD0, S_SD1, S_OI0, S_OI1, S_KEY, S_PERM, S_CHUNKS, S_ITEMS, S_NBR,
-    S_EVMAIL, S_EVTMP, S_EVRATE, S_EVSURF, S_HALO0, S_HALO1, S_COUNT
+    S_EVMAIL, S_EVTMP, S_EVRATE, S_EVSURF, S_HALO0, S_HALO1, S_PX, S_BX, S_COUNT
 };
 
 int kmc_ensure(KmcCtx* c, DBuf& b, size_t bytes);
@@ -174,6 +177,37 @@ struct LaunchScope {
         LaunchScope _ls((ctx), (fam));                                  \
         kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);     \
     } while (0)
+
+static inline double kmc_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Tiny utility kernels used instead of cudaMemsetAsync / cudaMemcpyAsync on the event path: with the default 8 hardware
+// connections those copy-engine operations BLOCK THE HOST while another stream's long kernel is running (measured: 1-2 ms
+// per call with 4-16 replicas in flight), kernel launches do not.  Results for the host go to pinned, device-mapped memory.
+#ifdef __CUDACC__
+static __global__ void k_zero_words(unsigned int* __restrict__ p, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+static __global__ void k_copy_words(unsigned int* __restrict__ dst, const unsigned int* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+// zero `bytes` (a multiple of 4) of device memory on the context's stream
+static inline int kmc_zero_async(KmcCtx* c, void* p, size_t bytes) {
+    const size_t n = bytes / 4;
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+    c->launches++;
+    k_zero_words<<<grid, 256, 0, c->stream>>>((unsigned int*)p, n);
+    return 0;
+}
+// copy `bytes` (a multiple of 4, small) from device memory to the pinned, device-mapped mailbox
+static inline int kmc_to_mailbox_async(KmcCtx* c, size_t mail_offset, const void* dev, size_t bytes) {
+    c->launches++;
+    k_copy_words<<<1, 128, 0, c->stream>>>((unsigned int*)((char*)c->h_mail_dev + mail_offset), (const unsigned int*)dev, (int)(bytes / 4));
+    return 0;
+}
+#endif
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

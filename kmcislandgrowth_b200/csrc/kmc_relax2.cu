@@ -24,7 +24,10 @@ static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
         CK(cudaFuncSetAttribute((const void*)k_relax2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
         c->relax2_smem_set = true;
     }
-    if (R.sync_mode == 0) {
+    if (R.sync_mode == 1 && !getenv("KMC_CLUSTER1")) {          // one block: a plain launch
+        k_relax2<<<1, R2_THREADS, sizeof(Relax2Smem), c->stream>>>(R);
+        CK(cudaGetLastError());
+    } else if (R.sync_mode == 0) {
         CK(cudaLaunchCooperativeKernel((const void*)k_relax2, dim3(blocks), dim3(R2_THREADS), args, sizeof(Relax2Smem), c->stream));
     } else {
         cudaLaunchConfig_t cfg{};
@@ -53,6 +56,7 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
                        const int* status_dev) {
     int blocks, sync_mode;
     relax2_shape(c, n, &blocks, &sync_mode);
+    const double t_a = kmc_now();
     if (c->item_cap == 0) c->item_cap = (size_t)n * 4 + (size_t)c->dp.ncell * 2 + 1024;
     if (const char* e = getenv("KMC_ITEM_CAP")) {      // tests: force the grow-and-relaunch path (once per context)
         if (!c->item_cap_forced) { c->item_cap = (size_t)std::max(1, atoi(e)); c->item_cap_forced = true; }
@@ -83,8 +87,11 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
     TRY(slot(c, S_RED, (size_t)blocks * 8, &R.red));
     unsigned char* sync;
     TRY(slot(c, S_SYNC, 512, &sync));
-    CK(cudaMemsetAsync(sync, 0, 512, c->stream));
+    TRY(kmc_zero_async(c, sync, 512));
     R.barrier = (unsigned int*)sync;
+    R.barrier2 = (unsigned int*)(sync + 4);
+    R.abort = (int*)(sync + 12);
+    R.unstaged = (int*)(sync + 28);
     R.hist = (unsigned long long*)(sync + 256);
     R.blk_ns = nullptr;
     R.need_rebuild = (int*)(sync + 16);
@@ -101,7 +108,11 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
         TRY(slot(c, S_TMP3, (size_t)2 * blocks, &R.blk_ns));
         CK(cudaMemsetAsync(R.blk_ns, 0, sizeof(unsigned long long) * 2 * blocks, c->stream));
     }
+    const double t_b = kmc_now();
     TRY(launch_relax2(c, R, blocks));
+    const double t_c = kmc_now();
+    c->enq_s[2] += t_b - t_a;
+    c->enq_s[3] += t_c - t_b;
     if (R.debug == 8) {
         std::vector<unsigned long long> h(2 * blocks);
         CK(cudaMemcpyAsync(h.data(), R.blk_ns, sizeof(unsigned long long) * 2 * blocks, cudaMemcpyDeviceToHost, c->stream));
@@ -115,7 +126,8 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
         }
     }
     // the 512-byte result block travels to the pinned mailbox behind the kernel; the caller synchronises
-    CK(cudaMemcpyAsync(c->h_mail, sync, 512, cudaMemcpyDeviceToHost, c->stream));
+    TRY(kmc_to_mailbox_async(c, 0, sync, 512));
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -152,6 +164,8 @@ int kmc_relax2_collect(KmcCtx* c, int n, KmcRelaxStats* stats, bool* again) {
                 (ph[0] + ph[32] + ph[33]) / nls * 1e-3, ph[1] / nls * 1e-3, ph[2] / nls * 1e-3, ph[3] / nls * 1e-3, ph[4] / nls * 1e-3, (ph[5] + ph[34] + ph[10] + ph[11] + ph[12] + ph[13] + ph[14] + ph[15]) / nls * 1e-3,
                 ph[6] / nls * 1e-3, ph[7] / nls * 1e-3, ph[8] ? ph[7] * 1e-3 / ph[8] : 0.0, (long long)ph[8], ph[9] / nls, (long long)ds->line_searches, (long long)ds->restarts, n, *(const int*)(hm + 20));
     }
+    if (ds->status == KMC_E_TIMEOUT)
+        return kmc_fail(KMC_E_TIMEOUT, "relaxation kernel: a device-side wait timed out (watchdog word %d: 1 grid barrier, 2 split barrier, 3 bulk copy)", *(const int*)(hm + 12));
     st.line_searches = ds->line_searches; st.restarts = ds->restarts; st.maxF = ds->maxF;
     st.final_threshold = ds->final_threshold; st.final_scale = ds->final_scale; st.status = ds->status;
     const long long per_sweep = (long long)visits + (c->dp.aa_mode == 0 ? (long long)n * (n - 1) / 2 : 0);

@@ -67,16 +67,18 @@ def run_replica_gpu(r, grid, n_events, device, max_line_searches=0, W=18, Hs=10,
 
 
 class LocalQueue(object):
-    """next replica id for a single process"""
+    """next replica id for a single process (thread safe: several engine threads may share it)"""
 
     def __init__(self, ids):
-        self.ids, self.pos = list(ids), 0
+        import threading
+        self.ids, self.pos, self.lock = list(ids), 0, threading.Lock()
 
     def __call__(self):
-        if self.pos >= len(self.ids):
-            return None
-        self.pos += 1
-        return self.ids[self.pos - 1]
+        with self.lock:
+            if self.pos >= len(self.ids):
+                return None
+            self.pos += 1
+            return self.ids[self.pos - 1]
 
 
 class StoreQueue(object):
@@ -142,18 +144,28 @@ class ReplicaBatch(object):
                     return
                 active.append(self._start(r, n_events))
 
+        prof = out["host_seconds"] = {"start": 0.0, "poll": 0.0, "finish": 0.0, "enqueue": 0.0, "idle_sweeps": 0}
+        t0 = time.perf_counter()
         refill()
+        prof["start"] += time.perf_counter() - t0
         while active:
             progressed = False
             for s in list(active):
-                if not s.ctx.event_ready():
+                t0 = time.perf_counter()
+                ready = s.ctx.event_ready()
+                t1 = time.perf_counter()
+                prof["poll"] += t1 - t0
+                if not ready:
                     continue
                 progressed = True
                 kind, hk, rtot, st = s.ctx.event_finish()
+                t2 = time.perf_counter()
+                prof["finish"] += t2 - t1
                 s.log.append((kind, hk, int(st.line_searches)))
                 s.t += 1
                 if s.t < s.n_events:
                     s.ctx.event_enqueue(self.sbins, s.us[s.t, 0], s.us[s.t, 1], self.max_ls)
+                    prof["enqueue"] += time.perf_counter() - t2
                 else:
                     ad = s.ctx.state_get()
                     out["log"][s.r], out["adatoms"][s.r] = s.log, ad
@@ -162,6 +174,7 @@ class ReplicaBatch(object):
                     self.pool.append(s.ctx)
                     refill()
             if not progressed:
+                prof["idle_sweeps"] += 1
                 time.sleep(0)           # yield the GIL / CPU while every replica is busy on the device
         return out
 
@@ -187,12 +200,34 @@ def run_sweep(grid, n_events, runner=run_replica_gpu, world_size=1, rank=0, devi
     return sorted((s for part in allr for s in part), key=lambda s: s["replica"])
 
 
-def run_sweep_batched(grid, n_events, device=0, width=16, queue=None, gather=None, **kw):
-    """The sweep on the batched engine: this process keeps `width` replicas in flight on `device`, taking replica ids from
-    `queue` (LocalQueue over all replicas by default, StoreQueue for a multi-process run).  -> summaries of all replicas."""
+def run_sweep_batched(grid, n_events, device=0, width=16, queue=None, gather=None, threads=1, **kw):
+    """The sweep on the batched engine: this process keeps `width` replicas in flight on `device` PER ENGINE THREAD, taking
+    replica ids from `queue` (LocalQueue over all replicas by default, StoreQueue for a multi-process run).  `threads` > 1
+    runs that many engines concurrently (the ctypes calls release the GIL): a host thread that the driver holds up while it
+    submits work does not stall the other engines' replicas.  -> summaries of all replicas."""
+    if queue is None:
+        queue = LocalQueue(range(len(grid)))
+    if threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def one(_):
+            b = ReplicaBatch((), grid, device=device, width=width, queue=queue, **kw)
+            try:
+                return b.run(n_events)
+            finally:
+                b.close()
+
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            parts = list(ex.map(one, range(threads)))
+        mine = [s for p in parts for s in p["summaries"]]
+        run_sweep_batched.last_host_seconds = parts[0]["host_seconds"]
+        allr = [mine] if gather is None else gather(mine)
+        return sorted((s for part in allr for s in part), key=lambda s: s["replica"])
     b = ReplicaBatch(range(len(grid)), grid, device=device, width=width, queue=queue, **kw)
     try:
-        mine = b.run(n_events)["summaries"]
+        res = b.run(n_events)
+        mine = res["summaries"]
+        run_sweep_batched.last_host_seconds = res["host_seconds"]
     finally:
         b.close()
     allr = [mine] if gather is None else gather(mine)
