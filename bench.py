@@ -28,6 +28,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # the replica sweep of the N > 1 extras keeps one hardware queue per stream
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -347,6 +349,9 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(tt[0]), float(tt[1])
 
+    sweep64 = domain_cfg5 = None
+    if world > 1 and not args.no_sharded:
+        sweep64, domain_cfg5 = sharded_configs(args, world, rank, progress)
     if rank == 0:
         peaks, peak_src = load_peaks()
         ls = [r["line_searches"] for r in recs]
@@ -387,11 +392,33 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "prerelax": {"line_searches": int(prerelax_ls), "status": int(st.status), "seconds": round(t_pre, 3)},
             "fp64_peak_tflops_measured": fp64_peak_tflops,
+            "sweep64": sweep64, "domain_cfg5": domain_cfg5,
         }
         print(json.dumps(line))
     sim.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_configs(args, world, rank, progress):
+    """N > 1: the two configurations of BASELINE.json that shard (after the headline measurement, untimed for `value`):
+    configs[3] -- the 64-replica temperature x flux sweep on the batched engine with dynamic assignment; configs[4] -- the
+    4096x4096 substrate with bin-column domain decomposition (NCCL halo exchange).  -> (sweep64, domain_cfg5) on rank 0."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    sweep64 = domain_cfg5 = None
+    try:
+        import bench_sweep64
+        sweep64 = bench_sweep64.run(nev=args.sweep_events, width=16, tag="bench")
+        progress("sweep64 done")
+    except Exception as e:                      # a failure here must not take the headline line down
+        sweep64 = {"error": repr(e)[:300]}
+    try:
+        import bench_domain
+        domain_cfg5 = bench_domain.run("cfg5_4096x4096", reps=20, n_events=args.domain_events, max_ls=150)
+        progress("domain_cfg5 done")
+    except Exception as e:
+        domain_cfg5 = {"error": repr(e)[:300]}
+    return sweep64, domain_cfg5
 
 
 NCU_CAPTURE = os.path.join(ROOT, "profiles", "relax2_ncu_latest.json")
@@ -451,6 +478,9 @@ def main():
     ap.add_argument("--prerelax", type=int, default=200000, help="line-search bound of the untimed set-up relaxation (it converges before)")
     ap.add_argument("--ref-line-searches", type=int, default=30, help="line searches of the marginal-time CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sweep64 / domain_cfg5 extra measurements")
+    ap.add_argument("--sweep-events", type=int, default=30, help="events per replica of the sweep64 extra measurement")
+    ap.add_argument("--domain-events", type=int, default=6, help="events of the domain_cfg5 extra measurement")
     ap.add_argument("--no-flush", action="store_true", help="skip the 256 MB L2 flush between events")
     ap.add_argument("--record-fixture", action="store_true", help="record line searches per event of the seeded trajectory")
     args = ap.parse_args()

@@ -200,6 +200,8 @@ int kmc_event(KmcCtx* ctx, const KmcBins* sbins, double u0, double u1, int64_t m
 int kmc_set_event_mode(KmcCtx* ctx, int mode);
 int kmc_event_enqueue(KmcCtx* ctx, const KmcBins* sbins, double u0, double u1, int64_t max_line_searches);
 int kmc_event_finish(KmcCtx* ctx, int32_t* kind_out, int64_t* hop_k_out, double* rtot_out, KmcRelaxStats* stats);
+/* rate table -> selection (u0) -> placement (u1) without the relaxation (the caller relaxes, e.g. with a domain-decomposed loop) */
+int kmc_event_place(KmcCtx* ctx, const KmcBins* sbins, double u0, double u1, int32_t* kind_out, int64_t* hop_k_out, double* rtot_out);
 /* 1: the enqueued event has completed (kmc_event_finish returns at once), 0: still running, < 0: error */
 int kmc_event_ready(KmcCtx* ctx);
 /* temperature x flux sweeps (BASELINE configs[3]; per-replica constants: Constants.py:45-46, 2DGrowth.py:43): one event
@@ -207,6 +209,19 @@ int kmc_event_ready(KmcCtx* ctx);
  * replica r.  Returns the first non-zero status other than KMC_E_ITERCAP, else 0. */
 int kmc_events_batch(KmcCtx** ctxs, KmcBins** sbins, int32_t R, const double* u0, const double* u1, int64_t max_line_searches,
                      int32_t* kind_out, int64_t* hop_k_out, double* rtot_out, KmcRelaxStats* stats, int32_t* rc_out);
+
+/* ---- spatial domain decomposition over bin columns (BASELINE configs[4]; the reference has no counterpart) ----
+ * A rank's LOCAL configuration: xy[0 .. n_own) are the adatoms it owns, xy[n_own .. n) halo copies of the neighbouring
+ * ranks' boundary columns (Bins.py:54-70: one column each side, the seam pair across the periodic boundary).  Only own
+ * atoms are evaluated; the cell grid is the global one.  bins3x3 adatom sums only (aa_mode 1).
+ * kmc_domain_sweep: forces F_aa + F_as (Energy.py:62-75), site energies e_aa (stencil sum, self term 0) / e_as
+ * (Energy.py:174-181), rate and surface flag (2DGrowth.py:46-62,201-215) of the own atoms from ONE cell-list build;
+ * any output may be NULL.  kmc_domain_line_energies: this rank's share of RelaxEnergy (Energy.py:133-148) for the K
+ * candidates of a line search (2DGrowth.py:121,152); the all-reduce over the ranks gives the candidate energies. */
+int kmc_domain_sweep(KmcCtx* ctx, const double* xy, int64_t n, int64_t n_own, const KmcBins* sbins, double* f_out, double* e_aa,
+                     double* e_as, double* rate, uint8_t* is_surface, int mem);
+int kmc_domain_line_energies(KmcCtx* ctx, const double* xy, const double* dir, int64_t n, int64_t n_own, int32_t scale, int32_t K,
+                             const KmcBins* sbins, double* e_out, int mem);
 
 /* Measurement helpers (bench.py).  kmc_fp64_peak: non-tensor FP64 FMA rate of the device in TFLOP/s (register-resident
  * DFMA chains at full occupancy, best of `repeats` runs, CUDA events) -- the denominator of the pair kernels' FP-pipe

@@ -86,9 +86,12 @@ SIGNATURES = {
     "kmc_set_event_mode": (C.c_int, [_VP, C.c_int]),
     "kmc_event_enqueue": (C.c_int, [_VP, _VP, _D, _D, _I64]),
     "kmc_event_finish": (C.c_int, [_VP, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_D), C.POINTER(KmcRelaxStats)]),
+    "kmc_event_place": (C.c_int, [_VP, _VP, _D, _D, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_D)]),
     "kmc_event_ready": (C.c_int, [_VP]),
     "kmc_events_batch": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP), _I32, C.POINTER(_D), C.POINTER(_D), _I64, C.POINTER(_I32),
                                    C.POINTER(_I64), C.POINTER(_D), C.POINTER(KmcRelaxStats), C.POINTER(_I32)]),
+    "kmc_domain_sweep": (C.c_int, [_VP, _VP, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int]),
+    "kmc_domain_line_energies": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _I32, _I32, _VP, _VP, C.c_int]),
     "kmc_fp64_peak": (C.c_int, [_VP, _I32, C.POINTER(_D), C.POINTER(_D)]),
     "kmc_relax_diag": (C.c_int, [_VP, C.POINTER(_I64)]),
 }

@@ -182,23 +182,23 @@ static int pick_group(size_t atoms) {
 
 // ------------------------------------------------------------------------------------ internals (device pointers)
 static int forces_dev(KmcCtx* c, CellView ad, const int* which_cfg, const KmcBins* sb, int n, double2* faa, double2* fas,
-                      double2* fsum) {
+                      double2* fsum, int n_compute = -1) {
     if (n == 0) return 0;
     const int G = pick_group(n);
     const int ncell2 = c->dp.ncell + 2;
     const unsigned grid = cdiv((size_t)n * G, 256);
     CellView sub = view_of(sb);
     switch (G) {
-        case 32: LAUNCH(c, "sweep_forces", k_sweep_forces<32>, grid, 256, c->dp, ad, sub, n, which_cfg, ncell2, faa, fas, fsum); break;
-        case 16: LAUNCH(c, "sweep_forces", k_sweep_forces<16>, grid, 256, c->dp, ad, sub, n, which_cfg, ncell2, faa, fas, fsum); break;
-        case 8: LAUNCH(c, "sweep_forces", k_sweep_forces<8>, grid, 256, c->dp, ad, sub, n, which_cfg, ncell2, faa, fas, fsum); break;
-        default: LAUNCH(c, "sweep_forces", k_sweep_forces<4>, grid, 256, c->dp, ad, sub, n, which_cfg, ncell2, faa, fas, fsum); break;
+        case 32: LAUNCH(c, "sweep_forces", k_sweep_forces<32>, grid, 256, c->dp, ad, sub, n, which_cfg, ncell2, faa, fas, fsum, n_compute); break;
+        case 16: LAUNCH(c, "sweep_forces", k_sweep_forces<16>, grid, 256, c->dp, ad, sub, n, which_cfg, ncell2, faa, fas, fsum, n_compute); break;
+        case 8: LAUNCH(c, "sweep_forces", k_sweep_forces<8>, grid, 256, c->dp, ad, sub, n, which_cfg, ncell2, faa, fas, fsum, n_compute); break;
+        default: LAUNCH(c, "sweep_forces", k_sweep_forces<4>, grid, 256, c->dp, ad, sub, n, which_cfg, ncell2, faa, fas, fsum, n_compute); break;
     }
     CK(cudaGetLastError());
     return 0;
 }
 
-static int energy_dev(KmcCtx* c, CellView ad, const KmcBins* sb, int n, int B, double* d_e) {
+static int energy_dev(KmcCtx* c, CellView ad, const KmcBins* sb, int n, int B, double* d_e, int n_compute = -1) {
     if (n == 0) { CK(cudaMemsetAsync(d_e, 0, sizeof(double) * B, c->stream)); return 0; }
     const int G = pick_group((size_t)n * B);
     const int ncell2 = c->dp.ncell + 2;
@@ -210,10 +210,10 @@ static int energy_dev(KmcCtx* c, CellView ad, const KmcBins* sb, int n, int B, d
     dim3 grid(gx, B);
     CellView sub = view_of(sb);
     switch (G) {
-        case 32: LAUNCH(c, "sweep_energy", k_sweep_energy<32>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e); break;
-        case 16: LAUNCH(c, "sweep_energy", k_sweep_energy<16>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e); break;
-        case 8: LAUNCH(c, "sweep_energy", k_sweep_energy<8>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e); break;
-        default: LAUNCH(c, "sweep_energy", k_sweep_energy<4>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e); break;
+        case 32: LAUNCH(c, "sweep_energy", k_sweep_energy<32>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e, n_compute); break;
+        case 16: LAUNCH(c, "sweep_energy", k_sweep_energy<16>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e, n_compute); break;
+        case 8: LAUNCH(c, "sweep_energy", k_sweep_energy<8>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e, n_compute); break;
+        default: LAUNCH(c, "sweep_energy", k_sweep_energy<4>, grid, 256, c->dp, ad, sub, n, ncell2, partial, done, d_e, n_compute); break;
     }
     CK(cudaGetLastError());
     return 0;
@@ -223,8 +223,9 @@ static int energy_dev(KmcCtx* c, CellView ad, const KmcBins* sb, int n, int B, d
 // (`ad` = cell list of x).  d_e[KC] and *d_amin (first argmin) are device pointers; d_amin may be null.
 static const int LINE_BLOCKS = 148 * 8;
 static int line_energies_dev(KmcCtx* c, const double2* d_x, const double2* d_s, int n, double scale, CellView ad, const KmcBins* sb,
-                             double* d_e, int* d_amin) {
+                             double* d_e, int* d_amin, int n_compute = -1) {
     LineArgs A{};
+    A.n_compute = n_compute;
     A.P = c->dp; A.ad = ad; A.sub = view_of(sb); A.x = d_x; A.s = d_s; A.scale = scale; A.inv_step = 1.0 / (20.0 * scale); A.n = n;
     TRY(slot(c, S_FLAG, (size_t)n, &A.flag));
     TRY(slot(c, S_MOVERS, (size_t)n, &A.movers));
@@ -232,6 +233,14 @@ static int line_energies_dev(KmcCtx* c, const double2* d_x, const double2* d_s, 
     TRY(slot(c, S_LPART, (size_t)LINE_BLOCKS * KC, &A.partial));
     TRY(slot(c, S_FIX, (size_t)n * KC, &A.fix));
     A.e_out = d_e; A.amin_out = d_amin;
+    A.colrange = nullptr;
+    if (c->dp.nby > 64 && ad.start == (const int*)c->slots[S_START].p) {      // tall grid, scratch cell list of this call: occupied rows per column
+        int2* cr;
+        TRY(slot(c, S_COLR, (size_t)c->dp.nbx, &cr));
+        LAUNCH(c, "line_mark", k_colrange_init, cdiv(c->dp.nbx, 256), 256, cr, c->dp.nbx);
+        LAUNCH(c, "line_mark", k_colrange, cdiv(n, 256), 256, c->dp, (const int*)c->slots[S_CELLOF].p, n, cr);
+        A.colrange = cr;
+    }
     LAUNCH(c, "line_mark", k_line_mark, std::min(cdiv(n, 256), 1184u), 256, A);
     LAUNCH(c, "line_compact", k_line_compact, 1, 1024, A);
     LAUNCH(c, "line_energy", k_line_energy, LINE_BLOCKS, LT_THREADS, A);
@@ -451,6 +460,7 @@ int kmc_create(const KmcParams* p, int device, KmcCtx** out) {
     if (cudaMalloc(&c->st_n_dev, 64) != cudaSuccess) { kmc_destroy(c); return fail(KMC_E_CUDA, "cudaMalloc failed"); }
     cudaMemset(c->st_n_dev, 0, 64);
     if (const char* e = getenv("KMC_EVENT_MODE")) c->event_mode = atoi(e) ? 1 : 0;
+    c->debug_sync = getenv("KMC_SYNC_DEBUG") != nullptr;
     *out = c;
     return 0;
 }
@@ -842,6 +852,79 @@ int kmc_select(KmcCtx* c, const double* rate, const uint8_t* surf, int64_t n, do
     TRY(call.out(rtot, 1, S_OUT1, &drt));
     TRY(call.out(pj, (size_t)n + 1, S_OUT2, &dpj));
     TRY(kmc_select_dev(c, dr, dsf, (int)n, u, dres, drt, dpj));
+    return call.finish();
+}
+
+// ---------------------------------------------------------------- spatial domain decomposition (BASELINE configs[4])
+// One sweep of a rank's LOCAL configuration: the first n_own atoms of xy are the rank's own, the rest are halo copies
+// received from the neighbouring ranks (or far-away dummies).  ONE cell-list build serves the force sweep and the rate
+// table; only own atoms are evaluated.  Everything stays on the device (mem = KMC_DEVICE: no copy, no synchronisation).
+int kmc_domain_sweep(KmcCtx* c, const double* xy, int64_t n, int64_t n_own, const KmcBins* sb, double* f_out, double* e_aa, double* e_as,
+                     double* rate, uint8_t* surf, int mem) {
+    if (!c || !sb) return fail(KMC_E_ARG, "NULL argument");
+    if (n_own < 0 || n_own > n) return fail(KMC_E_ARG, "n_own must be in 0..n");
+    if (c->dp.aa_mode != 1) return fail(KMC_E_ARG, "domain decomposition needs aa_mode == 1 (bins3x3 adatom sums)");
+    if (n == 0) return 0;
+    Call call(c, mem);
+    const double* d;
+    double *df, *da, *ds, *dr;
+    uint8_t* dsf;
+    TRY(call.in(xy, (size_t)2 * n, S_IN0, &d));
+    TRY(call.out(f_out, (size_t)2 * n_own, S_OUT0, &df));
+    TRY(call.out(e_aa, (size_t)n_own, S_OUT1, &da));
+    TRY(call.out(e_as, (size_t)n_own, S_OUT2, &ds));
+    TRY(call.out(rate, (size_t)n_own, S_OUT3, &dr));
+    TRY(call.out(surf, (size_t)n_own, S_OUT4, &dsf));
+    CellView ad;
+    TRY(kmc_scratch_cells(c, (const double2*)d, (int)n, 1, &ad));
+    if (df) TRY(forces_dev(c, ad, nullptr, sb, (int)n, nullptr, nullptr, (double2*)df, (int)n_own));
+    if (da || ds || dr || dsf) {
+        const int G = pick_group((size_t)n);
+        const unsigned grid = cdiv((size_t)n * G, 256);
+        CellView sub = view_of(sb);
+        double* nd = nullptr; int* ni = nullptr; const uint8_t* nu = nullptr; double2* n2 = nullptr; unsigned long long* nc = nullptr;
+#define DD_RATES(GG) LAUNCH(c, "sweep_rates", k_sweep_rates<GG>, grid, 256, c->dp, ad, sub, (int)n, dr, dsf, nd, nd, nd, ni, ni, nu, nu, n2, nc, (int)n_own, da, ds)
+        switch (G) {
+            case 32: DD_RATES(32); break;
+            case 16: DD_RATES(16); break;
+            case 8: DD_RATES(8); break;
+            default: DD_RATES(4); break;
+        }
+#undef DD_RATES
+        CK(cudaGetLastError());
+    }
+    return call.finish();
+}
+
+// This rank's share of RelaxEnergy (Energy.py:133-148) for the K line-search candidates x + a*s/20/scale (2DGrowth.py:121,152)
+// of its local configuration: own atoms take half of each adatom pair term and all of their substrate terms; the sum
+// over the ranks (one all-reduce of K doubles) is the configuration energy of every candidate.
+int kmc_domain_line_energies(KmcCtx* c, const double* xy, const double* dir, int64_t n, int64_t n_own, int32_t scale, int32_t K,
+                             const KmcBins* sb, double* e_out, int mem) {
+    if (!c || !sb || !e_out) return fail(KMC_E_ARG, "NULL argument");
+    if (K < 1 || K > 1024 || scale < 1) return fail(KMC_E_ARG, "bad K or scale");
+    if (n_own < 0 || n_own > n) return fail(KMC_E_ARG, "n_own must be in 0..n");
+    if (c->dp.aa_mode != 1) return fail(KMC_E_ARG, "domain decomposition needs aa_mode == 1 (bins3x3 adatom sums)");
+    Call call(c, mem);
+    const double *dx, *ds;
+    double *de, *cand;
+    TRY(call.in(xy, (size_t)2 * n, S_IN0, &dx));
+    TRY(call.in(dir, (size_t)2 * n, S_IN1, &ds));
+    TRY(call.out(e_out, (size_t)K, S_OUT0, &de));
+    if (K == KC && n > 0) {      // the line-search engine: ONE cell list of the base positions, 20 candidates per pair in registers
+        CellView ad;
+        TRY(kmc_scratch_cells(c, (const double2*)dx, (int)n, 1, &ad));
+        TRY(line_energies_dev(c, (const double2*)dx, (const double2*)ds, (int)n, (double)scale, ad, sb, de, nullptr, (int)n_own));
+        return call.finish();
+    }
+    TRY(slot(c, S_CAND, (size_t)2 * n * K, &cand));
+    if (n > 0) {
+        dim3 g(cdiv(2 * n, 256), K);
+        LAUNCH(c, "misc_candidates", k_make_candidates, g, 256, dx, ds, (int)(2 * n), (int)K, (double)scale, cand);
+    }
+    CellView ad;
+    TRY(kmc_scratch_cells(c, (const double2*)cand, (int)n, K, &ad));
+    TRY(energy_dev(c, ad, sb, (int)n, K, de, (int)n_own));
     return call.finish();
 }
 

@@ -392,6 +392,18 @@ int kmc_event_finish(KmcCtx* c, int32_t* kind_out, int64_t* hop_k_out, double* r
     return 0;
 }
 
+// rate table -> selection (u0) -> placement (u1) of one event WITHOUT the relaxation (2DGrowth.py:318-329 up to the call of
+// Relaxation inside DepositAdatom / HopAtom): the driver of a domain-decomposed trajectory places the atom on the full
+// state and relaxes with its own (multi-GPU) loop.
+int kmc_event_place(KmcCtx* c, const KmcBins* sb, double u0, double u1, int32_t* kind_out, int64_t* hop_k_out, double* rtot_out) {
+    if (!c || !sb) return kmc_fail(KMC_E_ARG, "NULL argument");
+    if (c->ev_pending) return kmc_fail(KMC_E_ARG, "an enqueued event has not been finished (kmc_event_finish)");
+    DevGuard guard(c);
+    TRY(enqueue_placement(c, sb, u0, u1, -1, -1, false));
+    CK(cudaStreamSynchronize(c->stream));
+    return collect_placement(c, kind_out, hop_k_out, rtot_out);
+}
+
 // 1 when the enqueued event of this context has completed on the device (kmc_event_finish will not block), 0 when it is
 // still running, negative on error.  Lets one host thread keep many replicas in flight without lockstep.
 int kmc_event_ready(KmcCtx* c) {

@@ -104,6 +104,7 @@ struct KmcCtx {
     int select_mode = 0;            // 0: sequential-order sums up to 65536 atoms, block scan beyond; 1: always sequential; 2: always block scan
     int event_mode = 1;             // 1 (default): the whole event is enqueued without a host round trip; 0: host-stepped placement (cross-check)
     int sm_count = 148;
+    bool debug_sync = false;        // KMC_SYNC_DEBUG
     double enq_s[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // diagnostics (KMC_ENQ_TIMING): host seconds spent in the parts of kmc_event_enqueue
     int64_t diag[4] = {0, 0, 0, 0};  // counters of the last relaxation (kmc_relax_diag)
     // an event that was enqueued and not yet finished (kmc_event_enqueue / kmc_event_finish)
@@ -132,7 +133,7 @@ enum Slot {
     S_F, S_FAA, S_FAS, S_X0, S_XN, S_XNP, S_SN, S_TMP0, S_TMP1, S_TMP2, S_TMP3,
     S_FLAG, S_MOVERS, S_NMOV, S_LPART, S_FIX, S_AMIN, S_RED, S_SYNC,
     S_POS0, S_POS1, S_SD0, S_SD1, S_OI0, S_OI1, S_KEY, S_PERM, S_CHUNKS, S_ITEMS, S_NBR,
-    S_EVMAIL, S_EVTMP, S_EVRATE, S_EVSURF, S_HALO0, S_HALO1, S_PX, S_BX, S_COUNT
+    S_EVMAIL, S_EVTMP, S_EVRATE, S_EVSURF, S_HALO0, S_HALO1, S_PX, S_BX, S_COLR, S_COUNT
 };
 
 int kmc_ensure(KmcCtx* c, DBuf& b, size_t bytes);
@@ -172,10 +173,20 @@ struct LaunchScope {
     }
 };
 
+// KMC_SYNC_DEBUG=1: synchronise after every launch and name the kernel family that faulted (diagnostics)
+static inline void kmc_debug_sync(KmcCtx* c, const char* what) {
+    if (!c->debug_sync) return;
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) fprintf(stderr, "[kmc sync debug] %s -> %s\n", what, cudaGetErrorString(e));
+}
+
 #define LAUNCH(ctx, fam, kernel, grid, block, ...)                      \
     do {                                                                \
-        LaunchScope _ls((ctx), (fam));                                  \
-        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);     \
+        {                                                               \
+            LaunchScope _ls((ctx), (fam));                              \
+            kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); \
+        }                                                               \
+        kmc_debug_sync((ctx), #kernel);                                 \
     } while (0)
 
 static inline double kmc_now() {
@@ -199,12 +210,14 @@ static inline int kmc_zero_async(KmcCtx* c, void* p, size_t bytes) {
     const unsigned grid = (unsigned)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
     c->launches++;
     k_zero_words<<<grid, 256, 0, c->stream>>>((unsigned int*)p, n);
+    kmc_debug_sync(c, "k_zero_words");
     return 0;
 }
 // copy `bytes` (a multiple of 4, small) from device memory to the pinned, device-mapped mailbox
 static inline int kmc_to_mailbox_async(KmcCtx* c, size_t mail_offset, const void* dev, size_t bytes) {
     c->launches++;
     k_copy_words<<<1, 128, 0, c->stream>>>((unsigned int*)((char*)c->h_mail_dev + mail_offset), (const unsigned int*)dev, (int)(bytes / 4));
+    kmc_debug_sync(c, "k_copy_words (mailbox)");
     return 0;
 }
 #endif

@@ -130,7 +130,10 @@ static __global__ void k_bin_order(int n, int B, int ncell2, const int* __restri
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell2 - 1; c += gridDim.x * blockDim.x) {
         const int lo = st[c], hi = st[c + 1];
         int* a = sidx + (size_t)b * n + lo;
-        sort_indices(a, hi - lo);
+        // (the last cell holds the atoms outside the grid: nobody's stencil addresses it, so the order inside it is
+        // immaterial -- a large population there, e.g. the empty halo slots of a domain-decomposed configuration, is
+        // not sorted by this one thread)
+        if (!(c == ncell2 - 2 && hi - lo > 64)) sort_indices(a, hi - lo);
         for (int s = lo; s < hi; ++s) sxy[(size_t)b * n + s] = xy[(size_t)b * n + sidx[(size_t)b * n + s]];
     }
 }
@@ -144,7 +147,7 @@ template <int G>
 static __global__ void __launch_bounds__(256) k_sweep_forces(DevParams P, CellView ad_base, CellView sub, int n,
                                                       const int* __restrict__ which_cfg, int ncell2,
                                                       double2* __restrict__ f_aa, double2* __restrict__ f_as,
-                                                      double2* __restrict__ f_sum) {
+                                                      double2* __restrict__ f_sum, int n_compute = -1) {
     const int cfg = which_cfg ? *which_cfg : 0;
     CellView ad = ad_base;
     if (ad.start) ad.start += (size_t)cfg * ncell2;
@@ -152,12 +155,16 @@ static __global__ void __launch_bounds__(256) k_sweep_forces(DevParams P, CellVi
     if (ad.sidx) ad.sidx += (size_t)cfg * n;      // null sidx == identity order (aa_mode 0 needs no cell list)
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x & (G - 1);
-    const bool live = gid < n;
+    bool live = gid < n;
     double ax = 0, ay = 0, sx = 0, sy = 0;
     int idx = 0;
     if (live) {
-        const double2 pi = ad.sxy[gid];
         idx = ad.sidx ? ad.sidx[gid] : gid;
+        // domain decomposition: only the first n_compute atoms (the rank's own) are evaluated, the rest are halo copies
+        if (n_compute >= 0 && idx >= n_compute) live = false;
+    }
+    if (live) {
+        const double2 pi = ad.sxy[gid];
         const Stencil st = make_stencil(P, pi.x, pi.y);
         if (P.aa_mode == 0) {
             for (int s = lane; s < n; s += G) acc_force(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2, ax, ay);
@@ -182,7 +189,7 @@ static __global__ void __launch_bounds__(256) k_sweep_forces(DevParams P, CellVi
 template <int G>
 static __global__ void __launch_bounds__(256) k_sweep_energy(DevParams P, CellView ad_base, CellView sub, int n, int ncell2,
                                                       double* __restrict__ partial, unsigned int* __restrict__ done,
-                                                      double* __restrict__ e_out) {
+                                                      double* __restrict__ e_out, int n_compute = -1) {
     __shared__ double s_red[32];
     __shared__ bool s_last;
     const int b = blockIdx.y;
@@ -197,6 +204,15 @@ static __global__ void __launch_bounds__(256) k_sweep_energy(DevParams P, CellVi
         const double2 pi = ad.sxy[gid];
         const int idx = ad.sidx ? ad.sidx[gid] : gid;
         const Stencil st = make_stencil(P, pi.x, pi.y);
+        if (n_compute >= 0) {
+            // domain decomposition (bins3x3 only): an own atom takes HALF of each of its pair terms, the other half is taken
+            // by the partner -- on this rank when it is an own atom too, on its owner's rank when it is a halo copy; halo
+            // copies themselves contribute nothing here.  Summed over the ranks this is the configuration energy.
+            if (idx < n_compute) {
+                visit_stencil(P, ad, st, lane, G, [&](int s) { e += 0.5 * pair_energy(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2); });
+                visit_stencil(P, sub, st, lane, G, [&](int s) { e += pair_energy(P, pi.x, pi.y, sub.sxy[s], P.E_as, P.ras2); });
+            }
+        } else {
         if (P.aa_mode == 0) {
             for (int s = lane; s < n; s += G)
                 if ((ad.sidx ? ad.sidx[s] : s) > idx) e += pair_energy(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2);
@@ -206,6 +222,7 @@ static __global__ void __launch_bounds__(256) k_sweep_energy(DevParams P, CellVi
             });
         }
         visit_stencil(P, sub, st, lane, G, [&](int s) { e += pair_energy(P, pi.x, pi.y, sub.sxy[s], P.E_as, P.ras2); });
+        }
     }
     const double tot = block_sum(e, s_red);
     if (threadIdx.x == 0) {
@@ -256,7 +273,8 @@ static __global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellVie
                                                      // incremental update (kmc_rates_update): only atoms that moved or whose
                                                      // cell is marked are recomputed; their reference positions are refreshed
                                                      const uint8_t* __restrict__ dirty_cell = nullptr, const uint8_t* __restrict__ self_dirty = nullptr,
-                                                     double2* __restrict__ ref_xy = nullptr, unsigned long long* __restrict__ recomputed = nullptr) {
+                                                     double2* __restrict__ ref_xy = nullptr, unsigned long long* __restrict__ recomputed = nullptr,
+                                                     int n_compute = -1, double* __restrict__ e_aa_o = nullptr, double* __restrict__ e_as_o = nullptr) {
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x & (G - 1);
     bool live = gid < n;
@@ -266,7 +284,8 @@ static __global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellVie
     if (live) {
         pi = ad.sxy[gid];
         idx = ad.sidx[gid];
-        if (dirty_cell) {
+        if (n_compute >= 0 && idx >= n_compute) live = false;      // halo copy (domain decomposition)
+        if (live && dirty_cell) {
             int nx, ny;
             bin_index(P, pi.x, pi.y, nx, ny);
             const int cell = flat_cell(P, nx, ny);
@@ -304,6 +323,8 @@ static __global__ void __launch_bounds__(256) k_sweep_rates(DevParams P, CellVie
         if (is_surface) is_surface[idx] = surf ? 1 : 0;
         if (delta_u) delta_u[idx] = du;
         if (u_appx_o) u_appx_o[idx] = appx;
+        if (e_aa_o) e_aa_o[idx] = ua;
+        if (e_as_o) e_as_o[idx] = us;
         if (u_loc_o) u_loc_o[idx] = loc;
         if (n_a_o) n_a_o[idx] = ka;
         if (n_s_o) n_s_o[idx] = ks;

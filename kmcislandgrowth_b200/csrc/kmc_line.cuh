@@ -244,6 +244,10 @@ struct LineArgs {
     double* fix;                 // [n_movers][KC]
     double* e_out;               // [KC]
     int* amin_out;               // first argmin (ys.index(min(ys)))
+    const int2* colrange;        // optional [nbx]: lowest / highest occupied cell row of every column of `ad` (x > y: column empty); lets
+                                 // the home-cell loop skip the empty part of a tall grid (configs[4]: 1186 rows, ~6 occupied)
+    int n_compute;               // domain decomposition: atoms with index < n_compute are the rank's own, the rest halo copies; a pair
+                                 // counts with weight (own_i + own_j)/2, a substrate term with weight own_i (-1: every atom is own)
 };
 
 // ---- phase M: movers ---------------------------------------------------------------------------
@@ -255,7 +259,9 @@ __device__ __forceinline__ void line_mark_movers(const LineArgs& A, int gtid, in
         bin_index(A.P, p0.x, p0.y, nx0, ny0);
         bin_index(A.P, pe.x, pe.y, nx1, ny1);
         const bool in0 = nx0 >= 0 && nx0 < A.P.nbx && ny0 >= 0 && ny0 < A.P.nby;
-        A.flag[i] = (in0 && nx0 == nx1 && ny0 == ny1) ? 0 : 1;
+        // domain decomposition: a halo copy that starts outside the grid (an empty halo slot, or an atom nobody can see)
+        // takes no part at all -- flag 2: neither paired on the fast path nor evaluated as a mover
+        A.flag[i] = (A.n_compute >= 0 && i >= A.n_compute && !in0) ? 2 : ((in0 && nx0 == nx1 && ny0 == ny1) ? 0 : 1);
     }
 }
 
@@ -265,7 +271,7 @@ __device__ __forceinline__ void line_compact_movers(const LineArgs& A, int* s_sc
     const int per = (A.n + T - 1) / T;
     const int lo = t * per, hi = min(lo + per, A.n);
     int cnt = 0;
-    for (int i = lo; i < hi; ++i) cnt += A.flag[i];
+    for (int i = lo; i < hi; ++i) cnt += (A.flag[i] == 1);
     s_scan[t] = cnt;
     __syncthreads();
     for (int off = 1; off < T; off <<= 1) {
@@ -276,7 +282,7 @@ __device__ __forceinline__ void line_compact_movers(const LineArgs& A, int* s_sc
     }
     int pos = s_scan[t] - cnt;
     for (int i = lo; i < hi; ++i)
-        if (A.flag[i]) A.movers[pos++] = i;
+        if (A.flag[i] == 1) A.movers[pos++] = i;
     if (t == T - 1) *A.n_movers = s_scan[t];
     __syncthreads();
 }
@@ -285,6 +291,7 @@ __device__ __forceinline__ void line_compact_movers(const LineArgs& A, int* s_sc
 struct LineSmem {
     double hx[LT_HOME], hy[LT_HOME], hsx[LT_HOME], hsy[LT_HOME];
     int hslot[LT_HOME];                 // slot of the home atom, INT_MAX for movers (never paired here)
+    float hown[LT_HOME], town[LT_TILE]; // ownership (1 / 0) of the staged home / partner atoms (domain decomposition)
     double tx[LT_TILE], ty[LT_TILE], tsx[LT_TILE], tsy[LT_TILE];
     int tslot[LT_TILE];                 // same-cell partner: its slot (pair iff hslot < tslot); other cells: INT_MAX; movers: -1
     double red[32];
@@ -292,21 +299,49 @@ struct LineSmem {
 
 // process the staged tile against the staged home atoms
 __device__ __forceinline__ void line_tile_pairs(const LineArgs& A, LineSmem& S, int nh, int nt, double E, double r0sq,
-                                                double (&acc)[KC]) {
+                                                double (&acc)[KC], bool substrate = false) {
     const int total = nh * nt;
     for (int p = threadIdx.x; p < total; p += blockDim.x) {
         const int i = p % nh, j = p / nh;
         if (S.hslot[i] >= S.tslot[j]) continue;
+        double Ew = E;
+        if (A.n_compute >= 0) {          // share of this rank in the pair (own-own 1, own-halo 1/2, halo-halo 0; substrate: own 1)
+            const double w = substrate ? (double)S.hown[i] : 0.5 * (double)(S.hown[i] + S.town[j]);
+            if (w == 0.0) continue;
+            Ew = E * w;
+        }
         const double dx0 = put_in_box(S.tx[j] - S.hx[i], A.P.L, A.P.halfL);
         const double dy0 = S.ty[j] - S.hy[i];
-        pair_line(A.P, dx0, dy0, S.tsx[j] - S.hsx[i], S.tsy[j] - S.hsy[i], E, r0sq, acc);
+        pair_line(A.P, dx0, dy0, S.tsx[j] - S.hsx[i], S.tsy[j] - S.hsy[i], Ew, r0sq, acc);
     }
 }
 
 __device__ __forceinline__ void line_energy_cells(const LineArgs& A, LineSmem& S, int first_cell, int cell_stride,
                                                   double (&acc)[KC]) {
     const DevParams& P = A.P;
-    for (int c = first_cell; c < P.ncell; c += cell_stride) {
+    // home cells of this block: every cell_stride-th cell of the grid, or -- with the occupied row range of every column
+    // known -- every cell_stride-th COLUMN, rows [lowest, highest] only.  Both orders are functions of the data alone.
+    int col = first_cell, row = 0, row_hi = -1;
+    int c = first_cell - cell_stride;
+    for (;;) {
+        if (A.colrange) {
+            if (row > row_hi) {
+                bool found = false;
+                for (; col < P.nbx; col += cell_stride) {
+                    const int2 r = A.colrange[col];
+                    if (r.x <= r.y) { row = r.x; row_hi = r.y; found = true; break; }
+                }
+                if (!found) break;
+                c = col * P.nby + row;
+                col += cell_stride;
+            } else {
+                c += 1;
+            }
+            ++row;
+        } else {
+            c += cell_stride;
+            if (c >= P.ncell) break;
+        }
         const int hb = A.ad.start[c], he = A.ad.start[c + 1];
         if (hb == he) continue;
         const int cx = c / P.nby, cy = c % P.nby;
@@ -338,6 +373,7 @@ __device__ __forceinline__ void line_energy_cells(const LineArgs& A, LineSmem& S
                 S.hx[i] = p.x; S.hy[i] = p.y;
                 S.hsx[i] = s.x * A.inv_step; S.hsy[i] = s.y * A.inv_step;
                 S.hslot[i] = A.flag[idx] ? 0x7fffffff : slot;
+                S.hown[i] = (A.n_compute < 0 || idx < A.n_compute) ? 1.0f : 0.0f;
             }
             // ---- adatom partners (bins3x3 mode): cells c' >= c of the stencil, with multiplicity
             if (P.aa_mode != 0) {
@@ -359,6 +395,7 @@ __device__ __forceinline__ void line_energy_cells(const LineArgs& A, LineSmem& S
                                 S.tx[j] = p.x; S.ty[j] = p.y;
                                 S.tsx[j] = s.x * A.inv_step; S.tsy[j] = s.y * A.inv_step;
                                 S.tslot[j] = A.flag[idx] ? -1 : (c2 == c ? slot : 0x7fffffff);
+                                S.town[j] = (A.n_compute < 0 || idx < A.n_compute) ? 1.0f : 0.0f;
                             }
                             __syncthreads();
                             line_tile_pairs(A, S, nh, nt, P.E_a, P.ra2, acc);
@@ -385,7 +422,7 @@ __device__ __forceinline__ void line_energy_cells(const LineArgs& A, LineSmem& S
                         }
                         __syncthreads();
                         // movers carry hslot = INT_MAX > 0x7ffffffe, so they are skipped here as well
-                        line_tile_pairs(A, S, nh, nt, P.E_as, P.ras2, acc);
+                        line_tile_pairs(A, S, nh, nt, P.E_as, P.ras2, acc, true);
                     }
                 }
             }
@@ -434,14 +471,18 @@ __device__ __forceinline__ double line_fix_one(const LineArgs& A, int r, int a, 
     const bool in_grid = rx >= 0 && rx < P.nbx && ry >= 0 && ry < P.nby;
     const Stencil st = make_stencil(P, pm.x, pm.y);
     double e = 0.0;
+    const bool dd = A.n_compute >= 0;
+    const double own_m = (!dd || m < A.n_compute) ? 1.0 : 0.0;
     if (P.aa_mode != 0) {
         // non-mover partners keep their base cell; an in-grid mover both sees them and is seen by them
         // (symmetric stencil relation), an out-of-grid mover only sees partners with a higher index
         visit_stencil(P, A.ad, st, lane, 32, [&](int slot) {
             const int j = A.ad.sidx[slot];
             if (A.flag[j] || (!in_grid && j < m)) return;
+            const double w = dd ? 0.5 * (own_m + (j < A.n_compute ? 1.0 : 0.0)) : 1.0;
+            if (w == 0.0) return;
             const double2 pj = cand2(A.x[j], A.s[j], a, A.scale);
-            e += pair_energy(P, pm.x, pm.y, pj, P.E_a, P.ra2);
+            e += w * pair_energy(P, pm.x, pm.y, pj, P.E_a, P.ra2);
         });
         // mover - mover: the lower index sees the higher one if the latter's cell is in its stencil
         for (int r2 = r + 1 + lane; r2 < nm; r2 += 32) {
@@ -451,10 +492,12 @@ __device__ __forceinline__ double line_fix_one(const LineArgs& A, int r, int a, 
             bin_index(P, p2.x, p2.y, cx, cy);
             if (cx < 0 || cx >= P.nbx || cy < 0 || cy >= P.nby) continue;
             const int mult = stencil_multiplicity(P, st, cx, cy);
-            if (mult) e += mult * pair_energy(P, pm.x, pm.y, p2, P.E_a, P.ra2);
+            const double w = dd ? 0.5 * (own_m + (m2 < A.n_compute ? 1.0 : 0.0)) : 1.0;
+            if (mult) e += w * mult * pair_energy(P, pm.x, pm.y, p2, P.E_a, P.ra2);
         }
     }
-    visit_stencil(P, A.sub, st, lane, 32, [&](int slot) { e += pair_energy(P, pm.x, pm.y, A.sub.sxy[slot], P.E_as, P.ras2); });
+    if (own_m != 0.0)
+        visit_stencil(P, A.sub, st, lane, 32, [&](int slot) { e += pair_energy(P, pm.x, pm.y, A.sub.sxy[slot], P.E_as, P.ras2); });
     return group_sum<32>(e);
 }
 

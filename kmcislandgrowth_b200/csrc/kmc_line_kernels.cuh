@@ -6,6 +6,21 @@
 namespace kmc {
 
 // ================================================================================ standalone kernels
+// lowest / highest occupied cell row of every column (tall, mostly empty grids: the home-cell loop visits only these rows)
+static __global__ void __launch_bounds__(256) k_colrange_init(int2* __restrict__ cr, int nbx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nbx) cr[i] = make_int2(0x7fffffff, -1);
+}
+static __global__ void __launch_bounds__(256) k_colrange(DevParams P, const int* __restrict__ cell_of, int n, int2* __restrict__ cr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell_of[i];
+    if (c >= P.ncell) return;
+    const int cx = c / P.nby, cy = c - cx * P.nby;
+    atomicMin(&cr[cx].x, cy);
+    atomicMax(&cr[cx].y, cy);
+}
+
 static __global__ void __launch_bounds__(256) k_line_mark(LineArgs A) {
     line_mark_movers(A, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }

@@ -211,6 +211,8 @@ static __global__ void __launch_bounds__(256, 2) k_relax_persistent(RelaxArgs R)
     const int gwarp = gtid >> 5, nwarps = gthreads >> 5;
 
     LineArgs A{};
+    A.n_compute = -1;
+    A.colrange = nullptr;
     A.P = R.P; A.sub = R.sub; A.n = R.n;
     A.ad.start = R.start; A.ad.sxy = R.sxy; A.ad.sidx = R.sidx; A.ad.n = R.n;
     A.x = R.xn; A.s = R.sn;

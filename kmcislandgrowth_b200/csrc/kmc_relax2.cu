@@ -39,6 +39,7 @@ static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
         CK(cudaLaunchKernelEx(&cfg, k_relax2, R));
     }
     if (c->timing) { cudaEventRecord(eb, c->stream); c->recs.push_back({kmc_family_id(c, "relax_persistent"), ea, eb}); }
+    kmc_debug_sync(c, "k_relax2");
     return 0;
 }
 
@@ -89,11 +90,7 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
     TRY(slot(c, S_SYNC, 512, &sync));
     TRY(kmc_zero_async(c, sync, 512));
     R.barrier = (unsigned int*)sync;
-    R.barrier2 = (unsigned int*)(sync + 4);
     R.abort = (int*)(sync + 12);
-    R.unstaged = (int*)(sync + 28);
-    R.hist = (unsigned long long*)(sync + 256);
-    R.blk_ns = nullptr;
     R.need_rebuild = (int*)(sync + 16);
     R.n_items = (int*)(sync + 20);
     R.n_movers = (int*)(sync + 24);
@@ -165,7 +162,7 @@ int kmc_relax2_collect(KmcCtx* c, int n, KmcRelaxStats* stats, bool* again) {
                 ph[6] / nls * 1e-3, ph[7] / nls * 1e-3, ph[8] ? ph[7] * 1e-3 / ph[8] : 0.0, (long long)ph[8], ph[9] / nls, (long long)ds->line_searches, (long long)ds->restarts, n, *(const int*)(hm + 20));
     }
     if (ds->status == KMC_E_TIMEOUT)
-        return kmc_fail(KMC_E_TIMEOUT, "relaxation kernel: a device-side wait timed out (watchdog word %d: 1 grid barrier, 2 split barrier, 3 bulk copy)", *(const int*)(hm + 12));
+        return kmc_fail(KMC_E_TIMEOUT, "relaxation kernel: a device-side wait timed out (watchdog word %d: 1 grid barrier, 3 bulk copy)", *(const int*)(hm + 12));
     st.line_searches = ds->line_searches; st.restarts = ds->restarts; st.maxF = ds->maxF;
     st.final_threshold = ds->final_threshold; st.final_scale = ds->final_scale; st.status = ds->status;
     const long long per_sweep = (long long)visits + (c->dp.aa_mode == 0 ? (long long)n * (n - 1) / 2 : 0);

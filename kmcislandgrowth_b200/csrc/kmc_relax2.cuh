@@ -5,21 +5,27 @@
 // operands are staged in shared memory by TMA bulk copies requested one phase ahead), every sum is
 // formed in a fixed order (bit-reproducible runs); the 20 candidate energies of a pair are ONE
 // Taylor polynomial (kmc_line.cuh: pair_line_poly) whose coefficients are summed over the pairs;
-// the CG update and the mover flags of the next line are fused into the force phase, leaving TWO
-// full grid barriers per line search (|| below) and one split barrier (arrive early ... wait late):
+// the CG update and the mover flags of the next line are fused into the force phase, leaving three
+// grid barriers per line search:
 //
 //   E: polynomial / per-candidate sums over the work items; block 0: ordered mover list and, for
 //      up to R2_FIX_INLINE movers, their per-candidate evaluation                             ||
 //      [F: mover fix-up phase, only for more movers                                           ||]
-//   S: every block: sums over blocks, candidate energies, first argmin; x_np for ITS OWN AND ITS HALO slots from the
-//      staged x_n / s_n (shared memory: the force sweep needs no published x_np), own x_np -> global, top/bot/min-y
-//      partials; whether a mover changed cell at the winner is evaluated by every block from the global mover list
-//      (identical result everywhere, no flag to exchange).                           arrive(B)
-//      [rebuild of the sorted state when a mover really changed cell: wait(B) first, then as a separate collective]
-//   G: forces at x_np from shared memory (one pass, T/atoms lanes per atom), max|F|^2 partials; wait(B) -- polled by a
-//      control warp DURING the sweep, every block arrived long ago -- gives beta; s <- F + beta s, mover flags  ||
+//   S: sums over blocks, candidate energies, first argmin, x_np, top/bot/min-y partials, cell check ||
+//      [rebuild of the sorted state when a mover really changed cell at the winner]
+//   G: forces at x_np (one pass, T/atoms lanes per atom), max|F|^2 partials, s <- F + beta s,
+//      mover flags of the next line                                                           ||
 //   C: control (every block, identical arithmetic): converged / stalled / out of bounds / continue;
 //      a restart from the original positions reuses the sorted layout and F(x0) when it can
+//
+// Measured in round 2 and NOT adopted (git history, commit 18b40f1): a two-barrier variant -- every block forms the x_np of its
+// own AND its halo slots from staged x_n / s_n (two-segment stage at the periodic seam), so the force sweep needs no
+// published x_np; the beta partials travel through a split barrier whose release is issued by a control warp.  Steady
+// state 25.3 us per line search against 26.5 us here, but 100.5 against 101.5 events/s on the bench (restarts and re-sorts
+// take its slower fall-back path), and on configs[4] the first line search after a restart formed inconsistent halo copies
+// (found by a cross-check of the local copies against the published ones; cause not established).  Also measured and
+// rejected: exchanging the 27 energy partials "data as flag" (relaxed 8-byte stores polled against a sentinel, no fence):
+// 148 blocks polling the same cache lines serialise at the L2 slices -- 34.9 us per line search.
 #pragma once
 #include "kmc_line.cuh"
 #include "kmc_relax.cuh"
@@ -87,9 +93,7 @@ struct Relax2Args {
     double* fix;            // [n][KC]
     double* red;            // [gridDim][4] top, bot, miny, maxF
     unsigned int* barrier;
-    unsigned int* barrier2;     // split barrier B (arrive early, wait late)
     int* abort;                 // watchdog word: != 0 once a spin loop timed out
-    int* unstaged;              // != 0: some block's force neighbourhood does not fit shared memory (full barrier before G)
     int* need_rebuild;
     unsigned long long* pair_counter;
     int scale0;
@@ -110,9 +114,9 @@ struct Relax2Args {
 //    with release/acquire semantics (~0.2 us);
 //  - one block: __syncthreads (global writes of a block are visible to the block after it; L1 stays warm).
 // Watchdog: no spin loop of this kernel waits forever.  A poll that has not succeeded after R2_SPIN_NS raises the abort
-// word (first writer wins: 1 = grid barrier, 2 = split barrier, 3 = bulk-copy mbarrier) and falls through; every later
-// poll sees the word and falls through as well, the line search returns, and the launch ends with status KMC_E_TIMEOUT
-// instead of hanging the device (a hung cooperative kernel can only be removed by resetting the GPU).
+// word (first writer wins: 1 = grid barrier, 3 = bulk-copy mbarrier) and falls through; every later poll sees the word
+// and falls through as well, the line search returns, and the launch ends with status KMC_E_TIMEOUT instead of hanging
+// the device (a hung cooperative kernel can only be removed by resetting the GPU).
 constexpr unsigned long long R2_SPIN_NS = 4000000000ull;
 __device__ __forceinline__ bool relax2_spin_expired(const Relax2Args& R, unsigned long long t0, int who) {
     if (*(volatile int*)R.abort != 0) return true;
@@ -148,40 +152,6 @@ __device__ __forceinline__ bool relax2_barrier(const Relax2Args& R, unsigned int
     }
 }
 
-// Split barrier B: a block ARRIVES once its top / bot / min-y partials (and its x_np) are written and WAITS only when it
-// needs the other blocks' partials (beta, after the force sweep) -- by then every block has arrived.  The release that
-// publishes the block's writes (MEMBAR.ALL.GPU + ERRBAR: 1-2 us) is issued by the CONTROL warp, which owns no atoms, so
-// the sweeping warps never wait for it.  (Measured and rejected: exchanging the partials "data as flag" -- relaxed 8-byte
-// stores polled against a sentinel by every block.  Without any fence it was slower: 148 blocks polling the same few
-// cache lines of the late blocks' slots serialise at their L2 slices and delay the very stores they wait for.)
-//  - global mode: arrive = one red.release.gpu by one thread after a bar.sync; wait = acquire poll by ONE thread
-//    (relax2_poll_b), the caller synchronises the block afterwards;
-//  - cluster mode: barrier.cluster.arrive / .wait, executed by every thread;
-//  - one block: nothing to exchange (the caller's bar.sync orders the block's own writes).
-__device__ __forceinline__ void relax2_arrive_b_one(const Relax2Args& R) {        // ONE thread, after a bar.sync (global mode)
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(R.barrier2) : "memory");
-}
-__device__ __forceinline__ void relax2_poll_b(const Relax2Args& R, unsigned int epoch2) {      // one thread, global mode
-    const unsigned int target = (epoch2 + 1u) * gridDim.x;
-    unsigned int v;
-    const unsigned long long t0 = gtimer();
-    unsigned int spins = 0;
-    do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(R.barrier2) : "memory");
-        if ((++spins & 1023u) == 0 && relax2_spin_expired(R, t0, 2)) break;
-    } while ((int)(v - target) < 0);
-}
-// beta / min-y from the per-block partials (every block: same values, same order) -> ctl[0..2]; one warp
-__device__ __forceinline__ void relax2_beta_partials(const Relax2Args& R, double* ctl, int lane) {
-    double t2 = 0.0, b2 = 0.0, m2 = INFINITY;
-    for (int b = lane; b < (int)gridDim.x; b += 32) {
-        const double* o = R.red + (size_t)b * 4;
-        t2 += o[0]; b2 += o[1]; m2 = fmin(m2, o[2]);
-    }
-    t2 = group_sum<32>(t2); b2 = group_sum<32>(b2); m2 = group_min<32>(m2);
-    if (lane == 0) { ctl[0] = t2; ctl[1] = b2; ctl[2] = m2; }
-}
-
 constexpr int R2_STAGE = 1024;       // atoms of the neighbourhood staged in shared memory by the force phase (16 KB)
 
 constexpr int R2_FIX_INLINE = 2;     // up to this many movers are evaluated by block 0 inside the energy phase
@@ -190,8 +160,7 @@ constexpr int R2_NBRC = 80;          // atoms of the block's chunk whose stencil
 constexpr int R2_SUBSTAGE = 512;     // substrate atoms cached per block (static between rebuilds)
 
 struct Relax2Smem {
-    alignas(16) double2 stage[R2_STAGE];     // positions of slots [smin, smax): x_n by one TMA bulk copy, turned into x_np in place
-    alignas(16) double2 gdir[R2_STAGE];      // directions s_n of the same slots (bulk copy on the same mbarrier)
+    alignas(16) double2 stage[R2_STAGE];     // positions of slots [smin, smax): one TMA 1-D bulk copy per block and line search
     // energy phase: operands of this block's work items, slots [emin, emax): positions, directions, mover flags (three
     // bulk copies completing on mbar_e, requested as soon as the previous line search has published them)
     alignas(16) double2 epos[R2_STAGE];
@@ -212,7 +181,7 @@ struct Relax2Smem {
     WorkItem wit[R2_THREADS / 32][R2_WI];    // this block's warps' first work items (static dealing: valid until the next rebuild)
     alignas(8) unsigned long long mbar;      // mbarrier the bulk copy completes on
     alignas(8) unsigned long long mbar_e;    // mbarrier of the energy-phase copies
-    int smin, smax, smin1, smax1;
+    int smin, smax;
     int emin, emax, submin, submax;
     double e[R2_NE];
     int amin;
@@ -277,13 +246,12 @@ __device__ __forceinline__ Ranges partner_ranges(const DevParams& P, const int* 
 
 // ---- rebuild of the sorted state from `n` source elements (7 barriers) ---------------------------
 // src_s / src_oidx may be null (direction 0 / identity index).
-__device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double2* src_pos, const double2* src_s, const int* src_oidx,
+__device__ __forceinline__ bool relax2_rebuild(const Relax2Args& R, const double2* src_pos, const double2* src_s, const int* src_oidx,
                                                double2* dst_pos, double2* dst_s, int* dst_oidx, unsigned int& epoch, Relax2Smem& S, int nA) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const DevParams& P = R.P;
     for (int c = gtid; c < R.ncell2; c += gthreads) R.start[c] = 0;
-    if (gtid == 0) *R.unstaged = 0;
-    relax2_barrier(R, epoch);
+    if (relax2_barrier(R, epoch)) return true;
     for (int k = gtid; k < nA; k += gthreads) {
         int nx, ny;
         bin_index(P, src_pos[k].x, src_pos[k].y, nx, ny);
@@ -291,7 +259,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         R.key[k] = c;
         atomicAdd(&R.start[1 + c], 1);
     }
-    relax2_barrier(R, epoch);
+    if (relax2_barrier(R, epoch)) return true;
     if (blockIdx.x == 0) {
         const int T = blockDim.x, t = threadIdx.x;
         const int m = R.ncell2 - 1;
@@ -312,12 +280,12 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         __syncthreads();
         for (int i = t; i < R.ncell2; i += T) R.cursor[i] = R.start[i];
     }
-    relax2_barrier(R, epoch);
+    if (relax2_barrier(R, epoch)) return true;
     for (int k = gtid; k < nA; k += gthreads) {
         const int slot = atomicAdd(&R.cursor[R.key[k]], 1);
         R.perm[slot] = k;
     }
-    relax2_barrier(R, epoch);
+    if (relax2_barrier(R, epoch)) return true;
     // per cell: order by original index (deterministic), move the payload, count the work items.
     // One WARP per cell: cells of up to 32 atoms are ranked with shuffles (three dependent fetches in all); the
     // rest of the per-cell work below is done by lane 0.
@@ -405,7 +373,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         }
     }
     if (gtid == 0) R.cursor[0] = 0;
-    relax2_barrier(R, epoch);
+    if (relax2_barrier(R, epoch)) return true;
     if (blockIdx.x == 0) {      // inclusive scan of the per-cell item counts cursor[1..ncell]
         const int T = blockDim.x, t = threadIdx.x;
         const int m = P.ncell;
@@ -425,7 +393,7 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
         for (int i = lo; i < hi; ++i) { run += R.cursor[i]; R.cursor[i] = run; }
         if (t == T - 1) *R.n_items = S.u.e.scan[t];      // true total; the caller checks it against item_cap
     }
-    relax2_barrier(R, epoch);
+    if (relax2_barrier(R, epoch)) return true;
     for (int c = gtid; c < P.ncell; c += gthreads) {
         int k = R.cursor[c];
         const int kend = R.cursor[c + 1];
@@ -450,7 +418,8 @@ __device__ __forceinline__ void relax2_rebuild(const Relax2Args& R, const double
             }
         }
     }
-    relax2_barrier(R, epoch);
+    if (relax2_barrier(R, epoch)) return true;
+    return false;
 }
 
 // ---- E: work items --------------------------------------------------------------------------------
@@ -693,40 +662,6 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsi
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// primitives without the proxy fence (the caller issues ONE fence.proxy.async for a group of copies)
-__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy(void* smem_dst, const void* gsrc, unsigned int bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// two copies completing on one mbarrier phase
-__device__ __forceinline__ void bulk_load2(void* d0, const void* g0, unsigned int n0, void* d1, const void* g1, unsigned int n1,
-                                           unsigned long long* bar) {
-    asm volatile("fence.proxy.async;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(n0 + n1) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(d0)), "l"(g0), "r"(n0), "r"(smem_u32(bar)) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(d1)), "l"(g1), "r"(n1), "r"(smem_u32(bar)) : "memory");
-}
-// four copies completing on one mbarrier phase (a two-segment stage: positions and directions of both segments)
-__device__ __forceinline__ void bulk_load4(void* d0, const void* g0, unsigned int n0, void* d1, const void* g1, unsigned int n1,
-                                           void* d2, const void* g2, unsigned int n2, void* d3, const void* g3, unsigned int n3,
-                                           unsigned long long* bar) {
-    asm volatile("fence.proxy.async;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(n0 + n1 + n2 + n3) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(d0)), "l"(g0), "r"(n0), "r"(smem_u32(bar)) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(d1)), "l"(g1), "r"(n1), "r"(smem_u32(bar)) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(d2)), "l"(g2), "r"(n2), "r"(smem_u32(bar)) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(d3)), "l"(g3), "r"(n3), "r"(smem_u32(bar)) : "memory");
-}
 // three copies completing on one mbarrier phase (one arrive.expect_tx for their total size)
 __device__ __forceinline__ void bulk_load3(void* d0, const void* g0, unsigned int n0, void* d1, const void* g1, unsigned int n1,
                                            void* d2, const void* g2, unsigned int n2, unsigned long long* bar) {
@@ -760,21 +695,7 @@ __device__ __forceinline__ void mbar_wait(const Relax2Args& R, unsigned long lon
 // walked as ONE flat index space and eight neighbour positions are fetched before their arithmetic, so a sweep
 // costs one or two L2 round trips instead of one per column (after a grid barrier every first touch misses L1;
 // a dependent L2 access measures ~0.45 us here)
-// The staged neighbourhood of a block: one or two slot segments [a0, b0) and [a1, b1), a1 >= b0 (two at the periodic seam,
-// where the stencil of column 0 reaches column nbins_x - 2 and vice versa, Bins.py:66-69); stage index = slot - a0 for the
-// first segment, continuing after it for the second.  a1 == b1 == INT_MAX: no second segment.
-struct GStage {
-    int a0, b0, a1, b1;
-    __device__ __forceinline__ int len() const { return (b0 - a0) + (b1 - a1); }
-    __device__ __forceinline__ bool staged() const { return len() > 0 && len() <= 1024; }
-    __device__ __forceinline__ int shift() const { return a1 - b0; }                       // gap between the segments
-    __device__ __forceinline__ int index(int slot) const { return slot - a0 - (slot >= a1 ? a1 - b0 : 0); }
-    __device__ __forceinline__ int slot_of(int i) const { return i < b0 - a0 ? a0 + i : a1 + (i - (b0 - a0)); }
-    __device__ __forceinline__ bool holds(int slot) const { return (slot >= a0 && slot < b0) || (slot >= a1 && slot < b1); }
-};
-
-// `ptr[sl - (sl >= seg1 ? shift : 0)]`: seg1 / shift map a slot to its place in a two-segment stage (seg1 = INT_MAX: plain index)
-__device__ __forceinline__ void flat_forces(const DevParams& P, const double2* ptr, int seg1, int shift, int4 b, int4 e, int lane, int G, double xi, double yi,
+__device__ __forceinline__ void flat_forces(const DevParams& P, const double2* ptr, int4 b, int4 e, int lane, int G, double xi, double yi,
                                             double E, double r0sq, double& fx, double& fy, unsigned long long& visits) {
     const int c0 = e.x - b.x, c1 = c0 + (e.y - b.y), c2 = c1 + (e.z - b.z), tot = c2 + (e.w - b.w);
     const double E12 = 12.0 * E;
@@ -785,7 +706,7 @@ __device__ __forceinline__ void flat_forces(const DevParams& P, const double2* p
         for (int k = 0; k < R2_FB; ++k) {
             const int tk = min(t + k * G, tot - 1);
             const int sl = tk < c0 ? b.x + tk : (tk < c1 ? b.y + (tk - c0) : (tk < c2 ? b.z + (tk - c1) : b.w + (tk - c2)));
-            p[k] = ptr[sl - (sl >= seg1 ? shift : 0)];
+            p[k] = ptr[sl];
             far = far || !(fabs(p[k].x - xi) < P.L);
         }
         if (far || P.precision == 1) {      // |dx| >= L (atoms that drifted by a box length) or fp32 pair terms: the general form
@@ -832,7 +753,7 @@ __device__ __forceinline__ void relax2_item_range(const Relax2Args& R, int n_ite
 // Slot range covered by the stencils of this block's chunk of atoms.  The atoms are cell-sorted column-major and only
 // a few cells of a column are occupied, so the stencils of a contiguous chunk cover ONE contiguous slot range (three
 // adjacent columns) except at the periodic seam.  Valid until the next rebuild.
-__device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Smem& S, GStage& gs, ERange& er, int nA) {
+__device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Smem& S, int& smin, int& smax, ERange& er, int nA) {
     const int T = blockDim.x;
     {   // the block's work items: a contiguous range of the (home-cell ordered) list, dealt to its warps round robin; the
         // first R2_WI of every warp are cached.  Contiguous items = adjacent home cells = ONE contiguous slot range of
@@ -874,40 +795,23 @@ __device__ __forceinline__ void relax2_stage_range(const Relax2Args& R, Relax2Sm
     const int per = (nA + gridDim.x - 1) / gridDim.x;
     const int lo = blockIdx.x * per, hi = min(lo + per, nA);
     __syncthreads();
-    if (threadIdx.x == 0) { S.smin = 0x7fffffff; S.smax = -1; S.smin1 = 0x7fffffff; S.smax1 = -1; }
+    if (threadIdx.x == 0) { S.smin = 0x7fffffff; S.smax = -1; }
     __syncthreads();
-    const int half = nA / 2;            // ranges that begin in the upper half of the slot space go to the second segment
     if (R.P.aa_mode != 0) {
         for (int slot = lo + threadIdx.x; slot < hi; slot += T) {
             const int4 ab = R.nbr[4 * slot], ae = R.nbr[4 * slot + 1];
             if (ab.x < 0) continue;
-            int mn = 0x7fffffff, mx = -1, mn1 = 0x7fffffff, mx1 = -1;
-            auto add = [&](int rb, int re) {
-                if (re <= rb) return;
-                if (rb < half) { mn = min(mn, rb); mx = max(mx, re); }
-                else { mn1 = min(mn1, rb); mx1 = max(mx1, re); }
-            };
-            add(ab.x, ae.x); add(ab.y, ae.y); add(ab.z, ae.z); add(ab.w, ae.w);
+            int mn = 0x7fffffff, mx = -1;
+            if (ae.x > ab.x) { mn = min(mn, ab.x); mx = max(mx, ae.x); }
+            if (ae.y > ab.y) { mn = min(mn, ab.y); mx = max(mx, ae.y); }
+            if (ae.z > ab.z) { mn = min(mn, ab.z); mx = max(mx, ae.z); }
+            if (ae.w > ab.w) { mn = min(mn, ab.w); mx = max(mx, ae.w); }
             if (mx > mn) { atomicMin(&S.smin, mn); atomicMax(&S.smax, mx); }
-            if (mx1 > mn1) { atomicMin(&S.smin1, mn1); atomicMax(&S.smax1, mx1); }
         }
     } else if (threadIdx.x == 0 && hi > lo) { S.smin = 0; S.smax = nA; }
     __syncthreads();
-    {
-        int a0 = S.smin, b0 = S.smax, a1 = S.smin1, b1 = S.smax1;
-        const bool has0 = b0 > a0, has1 = b1 > a1;
-        if (has0 && has1 && a1 <= b0) { b0 = max(b0, b1); a1 = b1 = 0x7fffffff; }       // the two parts touch: one segment
-        else if (!has0 && has1) { a0 = a1; b0 = b1; a1 = b1 = 0x7fffffff; }
-        else if (!has1) { a1 = b1 = 0x7fffffff; }
-        if (!has0 && !has1) { a0 = b0 = 0; }
-        gs.a0 = a0; gs.b0 = b0; gs.a1 = a1; gs.b1 = b1;
-        if (!gs.staged()) { gs.a0 = gs.b0 = 0; gs.a1 = gs.b1 = 0x7fffffff; }
-    }
-    // a block with atoms whose neighbourhood is not staged (too large, generic stencils, diagnostics) cannot form the x_np of
-    // its halo slots locally: then every block takes the path with a full barrier between S and G (uniform decision,
-    // read after the next grid barrier).  The block's own slots must be part of the stage as well.
-    const bool own_in = (lo >= gs.a0 && hi <= gs.b0) || (lo >= gs.a1 && hi <= gs.b1) || (gs.a1 == gs.b0 && lo >= gs.a0 && hi <= gs.b1);
-    if (threadIdx.x == 0 && hi > lo && (!gs.staged() || R.debug == 6 || !own_in)) atomicOr(R.unstaged, 1);
+    smin = S.smin; smax = S.smax;
+    if (!(smax > smin && (smax - smin) <= R2_STAGE)) { smin = 0; smax = 0; }
 }
 
 __device__ __forceinline__ double group_sum_rt(double v, int G) {
@@ -917,13 +821,9 @@ __device__ __forceinline__ double group_sum_rt(double v, int G) {
 
 // Every block owns a contiguous chunk of slots (cell-sorted, so its atoms share one neighbourhood, kept in shared memory).
 // The chunk is processed in ONE pass with T/atoms lanes per atom (see below); larger chunks take several passes.
-// stage_mode 0: read the neighbourhood from global memory `pos` into the stage here (first sweep of a pass, after a rebuild,
-//               or when some block is unstaged); 1: S.stage already holds the positions of [smin, smax) (formed in the S phase).
-// wait_b: beta is not known yet -- it is taken from the exchanged partials of epoch `epoch2` AFTER the sweep (a control warp
-//         polls for them during the sweep).
 __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2* pos, double2* sdir, const int* oidx, int mode, double beta,
-                                              double scale, bool count_pairs, Relax2Smem& S, const GStage& gs,
-                                              int stage_mode, bool wait_b, unsigned int epoch2, int nA, unsigned long long* tm = nullptr) {
+                                              double scale, bool count_pairs, Relax2Smem& S, unsigned int& parity, int smin, int smax,
+                                              bool issue_here, int nA, unsigned long long* tm = nullptr) {
 #define GMARK(k)                                                                          \
     if (tm && threadIdx.x == 0 && blockIdx.x == R.phase_block) {                          \
         const unsigned long long _t = gtimer();                                           \
@@ -941,41 +841,25 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
     // The neighbourhood of this block's atoms [smin, smax) was determined after the last rebuild (relax2_stage_range);
     // its positions are fetched by ONE TMA bulk copy (issued here, or earlier by the caller so that the copy overlaps
     // the control arithmetic) and the sweep reads shared memory.
-    const bool staged = gs.staged() && R.debug != 6;
-    if (staged && stage_mode == 0) {     // not formed in the S phase (first sweep of a pass, after a rebuild, unstaged grids)
+    const bool staged = smax > smin && (smax - smin) <= R2_STAGE && R.debug != 6;
+    if (staged && issue_here) {          // not loaded ahead by the caller (first sweep of a pass, after a rebuild)
         __syncthreads();
-        for (int i = threadIdx.x; i < gs.len(); i += T) S.stage[i] = pos[gs.slot_of(i)];
+        for (int i = threadIdx.x; i < smax - smin; i += T) S.stage[i] = pos[smin + i];
         __syncthreads();
     }
-    const double2* npos = staged ? (S.stage - gs.a0) : pos;      // neighbour positions by slot (second segment: minus nshift)
-    const int nseg1 = staged ? gs.a1 : 0x7fffffff, nshift = staged ? gs.shift() : 0;
+    const double2* npos = staged ? (S.stage - smin) : pos;       // neighbour positions by slot
     // ONE pass for the block's chunk: every atom gets LPA = T / atoms lanes (7 for 68 atoms on 512 threads; not a power of
     // two, so the lane partials are summed through shared memory, in lane order: deterministic).  A second, smaller
     // round for the atoms a power-of-two split leaves over cost a full latency chain on nearly idle SMs.
     const int cnt = hi - lo;
-    // control warp (global barrier mode, chunks that leave a warp free): the last warp owns no atoms; it issues the release
-    // that publishes this block's partials, polls the split barrier B and reduces the beta partials WHILE the other warps
-    // sweep, so beta is in shared memory when they need it.  (The caller has synchronised the block after its writes.)
-    const bool ctl = wait_b && R.sync_mode == 0 && 2 * cnt <= T - 32;
-    const int Teff = ctl ? T - 32 : T;
-    const int LPA = max(1, min(32, Teff / max(cnt, 1)));
-    const int app = Teff / LPA;                               // atoms per pass
-    bool have_beta = !wait_b;
-    if (wait_b && !ctl) {                 // no control warp: arrive now (every thread in cluster mode, thread 0 in global mode)
-        if (R.sync_mode == 2) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        else if (R.sync_mode == 0 && threadIdx.x == 0) relax2_arrive_b_one(R);
-    }
-    if (ctl && threadIdx.x >= Teff) {
-        if (threadIdx.x == Teff) { relax2_arrive_b_one(R); relax2_poll_b(R, epoch2); }
-        __syncwarp();
-        relax2_beta_partials(R, S.ctl, threadIdx.x - Teff);
-    }
+    const int LPA = max(1, min(32, T / max(cnt, 1)));
+    const int app = T / LPA;                                  // atoms per pass
     for (int r0 = lo; r0 < hi; r0 += app) {
         const int G = LPA;
         const int grp = threadIdx.x / LPA;
         const int lane = threadIdx.x - grp * LPA;
         const int slot = r0 + grp;
-        const bool live = threadIdx.x < Teff && grp < app && slot < hi;
+        const bool live = grp < app && slot < hi;
         double ax = 0, ay = 0, sx = 0, sy = 0;
         double2 pi = make_double2(0, 0), so = make_double2(0, 0);
         int4 ab = make_int4(0, 0, 0, 0), ae = ab, sb = ab, se = ab;
@@ -987,15 +871,15 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
         }
         GMARK(34)
         if (live) {
-            pi = (staged && gs.holds(slot)) ? S.stage[gs.index(slot)] : pos[slot];
+            pi = (staged && slot >= smin && slot < smax) ? npos[slot] : pos[slot];
             if (ab.x >= 0) {        // stencil ranges cached at the last rebuild
                 if (P.aa_mode == 0) {
-                    for (int s = lane; s < nA; s += G) acc_force(P, pi.x, pi.y, npos[s], P.E_a, P.ra2, ax, ay);       // all pairs: one segment [0, n)
+                    for (int s = lane; s < nA; s += G) acc_force(P, pi.x, pi.y, npos[s], P.E_a, P.ra2, ax, ay);
                 } else {
-                    flat_forces(P, npos, nseg1, nshift, ab, ae, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
+                    flat_forces(P, npos, ab, ae, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay, visits);
                 }
                 GMARK(12)
-                flat_forces(P, R.sub.sxy, 0x7fffffff, 0, sb, se, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
+                flat_forces(P, R.sub.sxy, sb, se, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy, visits);
                 GMARK(13)
             } else {                // atoms outside the grid / y-wrapped stencils: generic walk from the raw position
                 const Stencil st = make_stencil(P, pi.x, pi.y);
@@ -1010,14 +894,7 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
         if (r0 != lo) __syncthreads();                          // the previous pass has read its partials
         S.u.g.fpa[threadIdx.x] = make_double2(ax, ay);
         S.u.g.fps[threadIdx.x] = make_double2(sx, sy);
-        if (!have_beta && !ctl) {                               // no control warp: wait now, then one warp reduces the partials
-            if (R.sync_mode == 2) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-            else if (R.sync_mode == 0) { if (threadIdx.x == 0) relax2_poll_b(R, epoch2); __syncthreads(); }
-            else __syncthreads();
-            if (threadIdx.x < 32) relax2_beta_partials(R, S.ctl, threadIdx.x);
-        }
         __syncthreads();
-        if (!have_beta) { beta = S.ctl[0] / S.ctl[1]; have_beta = true; }      // 2DGrowth.py:143-145
         if (live && lane == 0) {
             ax = ay = sx = sy = 0.0;
             for (int l = 0; l < LPA; ++l) {
@@ -1046,15 +923,6 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
         }
         GMARK(15)
     }
-    if (!have_beta) {       // a block without atoms still takes part in the split barrier and needs min-y for the control step
-        if (!ctl) {
-            if (R.sync_mode == 2) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-            else if (R.sync_mode == 0) { if (threadIdx.x == 0) relax2_poll_b(R, epoch2); __syncthreads(); }
-            else __syncthreads();
-            if (threadIdx.x < 32) relax2_beta_partials(R, S.ctl, threadIdx.x);
-        }
-        __syncthreads();
-    }
     if (mode == 1) {
         const double r_mf = block_max(mf, S.red);
         if (threadIdx.x == 0) R.red[(size_t)blockIdx.x * 4 + 3] = r_mf;
@@ -1079,12 +947,8 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     const int nA = R.n_dev ? *R.n_dev : R.n;                   // adatoms of this relaxation
     if (nA <= 0) return;
     unsigned int epoch = 0;
-    unsigned int epoch2 = 0;         // epoch of the split barrier B (one per line search)
-    unsigned int g_parity = 0;
-    bool g_inflight = false;         // copies of the force neighbourhood (x_n, s_n) requested and not yet waited for
-    bool g_fresh = false;            // ... and they are the operands of the NEXT line search
-    bool fast_g = false;             // every block forms the x_np of its halo slots locally: no barrier between S and G
-    GStage gs{0, 0, 0x7fffffff, 0x7fffffff};     // staged force neighbourhood of this block (relax2_stage_range)
+    unsigned int tma_parity = 0;
+    int st_min = 0, st_max = 0;      // staged slot range of this block (relax2_stage_range)
     int n_items_reg = 0;             // *R.n_items of the last rebuild
     ERange er{};                     // work items and staged operands of the energy phase (relax2_stage_range)
     unsigned int e_parity = 0;
@@ -1113,32 +977,13 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     unsigned long long t_mark = gtimer();
 
     // request the operands of an energy phase: positions, directions and mover flags of slots [emin, emax)
-    // request x_n and s_n of the force neighbourhood (the S phase turns them into x_np in place)
-    // request x_n and s_n of the force neighbourhood and / or the operands of an energy phase (positions, directions and
-    // mover flags of slots [emin, emax)): thread 0 issues the copies of both groups behind ONE proxy fence
-    auto issue_copies = [&](const double2* p, const double2* d, bool want_e, bool want_g) {
-        if (threadIdx.x == 0 && (want_e || want_g)) {
-            proxy_fence();
-            if (want_e) {
-                const unsigned int ne = (unsigned int)(er.emax - er.emin), nf = (ne + 15u) & ~15u;
-                mbar_expect(&S.mbar_e, ne * 32u + nf);
-                bulk_copy(S.epos, p + er.emin, ne * 16u, &S.mbar_e);
-                bulk_copy(S.edir, d + er.emin, ne * 16u, &S.mbar_e);
-                bulk_copy(S.eflag, R.flag + er.emin, nf, &S.mbar_e);
-            }
-            if (want_g) {
-                const unsigned int n0 = (unsigned int)(gs.b0 - gs.a0), n1 = (unsigned int)(gs.b1 - gs.a1);
-                mbar_expect(&S.mbar, (n0 + n1) * 32u);
-                bulk_copy(S.stage, p + gs.a0, n0 * 16u, &S.mbar);
-                bulk_copy(S.gdir, d + gs.a0, n0 * 16u, &S.mbar);
-                if (n1) {
-                    bulk_copy(S.stage + n0, p + gs.a1, n1 * 16u, &S.mbar);
-                    bulk_copy(S.gdir + n0, d + gs.a1, n1 * 16u, &S.mbar);
-                }
-            }
+    auto issue_e = [&](const double2* p, const double2* d) {
+        if (threadIdx.x == 0) {
+            const unsigned int ne = (unsigned int)(er.emax - er.emin);
+            bulk_load3(S.epos, p + er.emin, ne * 16u, S.edir, d + er.emin, ne * 16u, S.eflag, R.flag + er.emin, (ne + 15u) & ~15u, &S.mbar_e);
         }
-        if (want_e) { e_inflight = true; e_fresh = true; }
-        if (want_g) { g_inflight = true; g_fresh = true; }
+        e_inflight = true;
+        e_fresh = true;
     };
     // One line search.  With `decide` the call first settles, from the max|F|^2 of the PREVIOUS line search, whether there is a
     // line search at all (2DGrowth.py:131-140,162-164): the partials are requested at the start of the energy phase and read
@@ -1160,11 +1005,9 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             const int b = lane + 32 * i;
             mfv[i] = (decide && warp == 0 && b < nblk) ? R.red[(size_t)b * 4 + 3] : 0.0;
         }
-        {   // first line of a pass: nothing was requested ahead
-            const bool want_e = er.emax > er.emin && !e_fresh, want_g = fast_g && gs.staged() && !g_fresh;
-            if (want_e && e_inflight) { mbar_wait(R, &S.mbar_e, e_parity); e_parity ^= 1u; }
-            if (want_g && g_inflight) { mbar_wait(R, &S.mbar, g_parity); g_parity ^= 1u; }
-            issue_copies(pos, sdir, want_e, want_g);
+        if (er.emax > er.emin && !e_fresh) {            // first line of a pass: nothing was requested ahead
+            if (e_inflight) { mbar_wait(R, &S.mbar_e, e_parity); e_parity ^= 1u; }
+            issue_e(pos, sdir);
         }
         if (blockIdx.x == 0) {          // ordered list of mover slots
             const int T = blockDim.x, t = threadIdx.x;
@@ -1271,11 +1114,15 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         if (relax2_barrier(R, epoch)) return 4;
         PHASE2_MARK(1)
         // ---------------- F
-        // everything the S phase needs from global memory is requested here, in one L2 round trip: the mover count and
-        // this warp's share of the partial sums
+        // everything the S phase needs is requested here, in one L2 round trip: the mover count, this thread's atom
+        // (the block's chunk of slots, as in the force phase) and this warp's share of the partial sums
         const int nm = *R.n_movers;
         const int per = (nA + nblk - 1) / nblk;
         const int lo = blockIdx.x * per, hi = min(lo + per, nA);
+        const int myslot = lo + threadIdx.x;
+        double2 pre_p = make_double2(0, 0), pre_s = make_double2(0, 0);
+        unsigned int pre_f = 0;
+        if (myslot < hi) { pre_p = pos[myslot]; pre_s = sdir[myslot]; pre_f = R.flag[myslot]; }
         constexpr int WPB = R2_THREADS / 32, NEW = (R2_NE + WPB - 1) / WPB;
         double pv[NEW];
 #pragma unroll
@@ -1292,7 +1139,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 const double e = relax2_fix_one(R, pos, sdir, oidx, dscale, w / KC, w % KC, lane, nA);
                 if (lane == 0) R.fix[w] = e;
             }
-            relax2_barrier(R, epoch);
+            if (relax2_barrier(R, epoch)) return 4;
             PHASE2_MARK(2)
         }
         // ---------------- S
@@ -1322,113 +1169,94 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         }
         __syncthreads();
         const int amin = S.amin;
-        // Did a mover really change cell at the winner?  Every block answers from the global (ordered) mover list with the
-        // same arithmetic -- a uniform decision without a flag to publish (x_n, s_n and the list are stable until wait(B)).
-        int moved = 0;
-        for (int r = threadIdx.x; r < nm; r += R2_THREADS) {
-            const int m = R.movers[r];
-            const double2 p = cand2(pos[m], sdir[m], amin, dscale);
-            int nx, ny;
-            bin_index(P, p.x, p.y, nx, ny);
-            if (flat_cell(P, nx, ny) != R.cellof[m]) moved = 1;
-        }
-        // x_np (2DGrowth.py:123,155): own slots -> global; with fast_g also the halo slots, in place in shared memory
         double top = 0.0, bot = 0.0, my = INFINITY;
-        const bool local_np = fast_g && gs.staged();
-        if (local_np) {
-            mbar_wait(R, &S.mbar, g_parity);
-            g_parity ^= 1u;
-            g_inflight = false;
-            g_fresh = false;
-            const int scnt = gs.len();
-            for (int i = threadIdx.x; i < scnt; i += R2_THREADS) {
-                const double2 p0 = S.stage[i];
-                const double2 p = cand2(p0, S.gdir[i], amin, dscale);
-                S.stage[i] = p;
-                const int slot = gs.slot_of(i);
-                if (slot >= lo && slot < hi) {
-                    posn[slot] = p;
-                    top += p.x * (p.x - p0.x) + p.y * (p.y - p0.y);                // :143
-                    bot += p0.x * p0.x + p0.y * p0.y;                              // :144
-                    my = fmin(my, p.y);                                            // :137
-                }
-            }
-        } else {
-            for (int slot = lo + threadIdx.x; slot < hi; slot += R2_THREADS) {
-                const double2 p0 = pos[slot];
-                const double2 p = cand2(p0, sdir[slot], amin, dscale);
-                posn[slot] = p;
-                top += p.x * (p.x - p0.x) + p.y * (p.y - p0.y);
-                bot += p0.x * p0.x + p0.y * p0.y;
-                my = fmin(my, p.y);
+        for (int slot = myslot; slot < hi; slot += R2_THREADS) {
+            const bool first = slot == myslot;
+            const double2 p0 = first ? pre_p : pos[slot];
+            const double2 p = cand2(p0, first ? pre_s : sdir[slot], amin, dscale);
+            posn[slot] = p;
+            top += p.x * (p.x - p0.x) + p.y * (p.y - p0.y);                // :143
+            bot += p0.x * p0.x + p0.y * p0.y;                              // :144
+            my = fmin(my, p.y);                                            // :137
+            if (first ? pre_f : (unsigned int)R.flag[slot]) {
+                int nx, ny;
+                bin_index(P, p.x, p.y, nx, ny);
+                if (flat_cell(P, nx, ny) != R.cellof[slot]) *R.need_rebuild = 1;
             }
         }
         {   // one fused block reduction (fixed tree) of the three partials
             top = group_sum<32>(top); bot = group_sum<32>(bot); my = group_min<32>(my);
             if (lane == 0) { S.u.e.wred[warp][0] = top; S.u.e.wred[warp][1] = bot; S.u.e.wred[warp][2] = my; }
-        }
-        const int rebuild_now = __syncthreads_or(moved);
-        if (warp == 0) {
-            double t2 = lane < WPB ? S.u.e.wred[lane][0] : 0.0, b2 = lane < WPB ? S.u.e.wred[lane][1] : 0.0, m2 = lane < WPB ? S.u.e.wred[lane][2] : INFINITY;
-            t2 = group_sum<32>(t2); b2 = group_sum<32>(b2); m2 = group_min<32>(m2);
-            if (lane == 0) {
-                double* o = R.red + (size_t)blockIdx.x * 4;
-                o[0] = t2; o[1] = b2; o[2] = m2;
+            __syncthreads();
+            if (warp == 0) {
+                double t2 = lane < WPB ? S.u.e.wred[lane][0] : 0.0, b2 = lane < WPB ? S.u.e.wred[lane][1] : 0.0, m2 = lane < WPB ? S.u.e.wred[lane][2] : INFINITY;
+                t2 = group_sum<32>(t2); b2 = group_sum<32>(b2); m2 = group_min<32>(m2);
+                if (lane == 0) {
+                    double* o = R.red + (size_t)blockIdx.x * 4;
+                    o[0] = t2; o[1] = b2; o[2] = m2;
+                }
             }
         }
-        __syncthreads();            // the block's x_np and partials are written: whoever arrives at B for it may release them
         PHASE2_MARK(3)
+        if (relax2_barrier(R, epoch)) return 4;
+        PHASE2_MARK(4)
         if (R.debug == 8 && threadIdx.x == 0) t_blk = gtimer();
-        // ---------------- rebuild (rare) + G
-        bool restaged = false;
-        const bool local_ok = fast_g && !rebuild_now;       // uniform over the grid (a block without atoms has nothing staged, and nothing to sweep)
-        double beta = 0.0;
-        if (!local_ok) {
-            // every x_np must be published before the rebuild / before a sweep that reads the neighbourhood from global memory
-            if (relax2_barrier(R, epoch)) return 4;
-            // x_np is published: fetch this block's neighbourhood (two elements per thread) together with the beta partials
-            // -- ONE L2 round trip, one bar.sync
-            const bool restage = !rebuild_now && gs.staged() && R.debug != 6;
-            const int scnt = restage ? gs.len() : 0;
+        // x_np is published: fetch this block's neighbourhood [st_min, st_max) (two elements per thread) together with
+        // the beta partials -- ONE L2 round trip, one __syncthreads -- into shared memory for the force sweep.
+        // (A TMA bulk copy of the same ~5 KB took ~1.9 us from issue to completion here; plain loads take ~0.7 us.)
+        const bool early = st_max > st_min && R.debug != 6;
+        const int rebuild_now = *R.need_rebuild;             // requested with the rest
+        {
+            const int scnt = st_max - st_min;
             double2 sv[R2_STAGE / R2_THREADS];
 #pragma unroll
-            for (int kk = 0; kk < R2_STAGE / R2_THREADS; ++kk) {
-                const int i = threadIdx.x + kk * R2_THREADS;
-                sv[kk] = i < scnt ? posn[gs.slot_of(i)] : make_double2(0.0, 0.0);
+            for (int k = 0; k < R2_STAGE / R2_THREADS; ++k) {
+                const int i = threadIdx.x + k * R2_THREADS;
+                sv[k] = (early && i < scnt) ? posn[st_min + i] : make_double2(0.0, 0.0);
             }
-            if (threadIdx.x < 32) relax2_beta_partials(R, S.ctl, threadIdx.x);
+            // every block: beta and min-y from the same partials in the same order
+            if (threadIdx.x < 32) {
+                double t2 = 0.0, b2 = 0.0, m2 = INFINITY;
+                for (int b = lane; b < nblk; b += 32) {
+                    const double* o = R.red + (size_t)b * 4;
+                    t2 += o[0]; b2 += o[1]; m2 = fmin(m2, o[2]);
+                }
+                t2 = group_sum<32>(t2); b2 = group_sum<32>(b2); m2 = group_min<32>(m2);
+                if (lane == 0) { S.ctl[0] = t2; S.ctl[1] = b2; S.ctl[2] = m2; }
+            }
 #pragma unroll
-            for (int kk = 0; kk < R2_STAGE / R2_THREADS; ++kk) {
-                const int i = threadIdx.x + kk * R2_THREADS;
-                if (i < scnt) S.stage[i] = sv[kk];
+            for (int k = 0; k < R2_STAGE / R2_THREADS; ++k) {
+                const int i = threadIdx.x + k * R2_THREADS;
+                if (early && i < scnt) S.stage[i] = sv[k];
             }
-            __syncthreads();
-            beta = S.ctl[0] / S.ctl[1];                                           // :143-145
-            restaged = restage;
         }
-        PHASE2_MARK(4)
+        __syncthreads();
+        const double beta = S.ctl[0] / S.ctl[1];                          // :143-145
+        PHASE2_MARK(10)
+        // ---------------- rebuild (rare) + G
+        bool issue_here = false;
         if (rebuild_now) {
-            relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S, nA);
+            issue_here = true;
+            if (relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S, nA)) return 4;
+            if (gtid == 0) *R.need_rebuild = 0;
             if (*R.n_items > R.item_cap) overflow = true;
             ++rebuilds;
             layout_x0 = false;
-            relax2_stage_range(R, S, gs, er, nA);
+            relax2_stage_range(R, S, st_min, st_max, er, nA);
             n_items_reg = *R.n_items;
             PHASE2_MARK(7)
             cs ^= 1;          // the rebuilt x_np now lives in pos[cur]: make it the "next" buffer by flipping cur
             cur ^= 1;
         }
         PHASE2_MARK(11)
-        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, gs, (local_ok || restaged) ? 1 : 0, local_ok, epoch2, nA, &t_mark);
-        if (local_ok) ++epoch2;                     // one arrive + one wait per use of the split barrier
+        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, tma_parity, st_min, st_max, issue_here, nA, &t_mark);
         PHASE2_MARK(5)
         if (R.debug == 8 && threadIdx.x == 0) R.blk_ns[2 * blockIdx.x + 1] += gtimer() - t_blk;
         if (relax2_barrier(R, epoch)) return 4;
         PHASE2_MARK(6)
-        if (rebuild_now) fast_g = (*R.unstaged == 0) && R.debug != 6 && R.debug != 9;      // set by relax2_stage_range, published by the barrier above
         // the next line search (if there is one) starts from x_np with the directions and flags just published: request
         // its operands now, the copies land while the control arithmetic runs
-        issue_copies(R.pos[cur ^ 1], R.sdir[cs], er.emax > er.emin, fast_g && gs.staged());
+        if (er.emax > er.emin) issue_e(R.pos[cur ^ 1], R.sdir[cs]);
         ++ls;
         return 0;
     };
@@ -1436,10 +1264,8 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     for (;;) {                                                         // one pass == one (recursive) call of Relaxation
         if (scale > 1024) { scale = 16; threshold *= 10; }              // :111-113
         e_fresh = false;                                                // the pass rewrites positions, directions and flags
-        g_fresh = false;
         const int per = (nA + nblk - 1) / nblk;
         const int lo = blockIdx.x * per, hi = min(lo + per, nA);
-        const bool layout_x0_reused = layout_x0;
         if (layout_x0) {
             // restart from the ORIGINAL positions while the sorted layout is still the one built from them: the cell list,
             // the work items and the first direction dx0 = F(x0) are unchanged (only the mover flags depend on the new
@@ -1455,18 +1281,17 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 R.flag[slot] = mover_flag(P, p, s0, (double)scale);
             }
         } else {
-            relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S, nA);
+            if (relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S, nA)) { status = -8; break; }
             if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
-            relax2_stage_range(R, S, gs, er, nA);
+            relax2_stage_range(R, S, st_min, st_max, er, nA);
             n_items_reg = *R.n_items;
-            relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, gs, 0, false, 0u, nA);   // dx0, sn = dx0  :120,125
+            relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true, nA);   // dx0, sn = dx0  :120,125
             first_pass = false;
             __syncthreads();
             for (int slot = lo + threadIdx.x; slot < hi; slot += R2_THREADS) R.sdir[cs ^ 1][slot] = R.sdir[cs][slot];     // dx0, kept for the restarts
             layout_x0 = true;
         }
         if (relax2_barrier(R, epoch)) { status = -8; break; }
-        if (!layout_x0_reused) fast_g = (*R.unstaged == 0) && R.debug != 6 && R.debug != 9;       // set by relax2_stage_range, published by the barrier above
         int code = line_search(false);                                  // :121-129
         if (overflow) { status = -4; break; }
         stall_check = false;                                            // lastmaxF = maxF after the first line search (:130)
@@ -1484,7 +1309,6 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         scale *= 2;
     }
     if (e_inflight) mbar_wait(R, &S.mbar_e, e_parity);                     // no copy may be pending when the block exits
-    if (g_inflight) mbar_wait(R, &S.mbar, g_parity);
     // result: PutAllInBox(x_np) in the original order   (:166)
     if (status != -4 && status != -8) {
         const double2* posn = R.pos[cur ^ 1];

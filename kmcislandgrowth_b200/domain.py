@@ -240,3 +240,233 @@ class DomainSweeps(object):
         local_rows = np.asarray(local_rows, dtype=np.float64)
         cols = [self._gather_dense(local_rows[:, k], np.float64) for k in range(local_rows.shape[1])]
         return np.column_stack(cols)
+
+
+# ================================================================================================================
+# Device-resident decomposition (the product path for BASELINE configs[4]): positions, directions, halos and every
+# partial result stay in HBM; the ranks talk through NCCL point-to-point / small collectives on device tensors
+# (NVLink), the host only launches.  torch is used for buffers, a few elementwise operations on them and
+# torch.distributed -- the pair sweeps are the library's kernels (kmc_domain_sweep, kmc_domain_line_energies).
+# ================================================================================================================
+DUMMY_Y = 1.0e9          # a halo slot that carries no atom: far outside the cell grid (seen by nobody, evaluated by nobody)
+
+
+class DeviceDomain(object):
+    """One large configuration spread over the ranks of a process group by bin columns.
+
+    Layout of a rank's LOCAL configuration (the argument of the library's domain entry points):
+        [ own atoms (n_own) | slots for rank s1's atoms | slots for rank s2's atoms | ... ]
+    A neighbour sends ALL its own atoms with those outside the requested boundary columns replaced by a dummy position
+    (fixed message size: no compaction, no count exchange, no host synchronisation; a message is n_own x 16 or 32 bytes,
+    i.e. KBs -- the exchange is latency bound, not bandwidth bound, so the padding is free).  Ownership is fixed by the
+    columns at partition time (once per event); halo membership follows the current columns at every exchange.
+    The substrate is static and replicated (268 MB for the 4096x4096 substrate of configs[4]: 0.15 % of one B200's HBM)."""
+
+    def __init__(self, gv, substrate, adatoms, rank=0, world=1, device=0, dist=None, ctx=None, sbins=None):
+        import torch
+        from . import runtime
+        if int(getattr(gv, "aa_mode", 0)) != 1:
+            raise ValueError("domain decomposition needs aa_mode == 1 (bins3x3 adatom sums); got aa_mode=%r" % getattr(gv, "aa_mode", 0))
+        self.torch, self.gv, self.rank, self.world, self.dist = torch, gv, rank, world, dist
+        self.dev = torch.device("cuda", device)
+        self.dec = Decomposition(gv, world)
+        self.ctx = ctx if ctx is not None else runtime.Context(runtime.params_from(gv), device)
+        self.own_ctx = ctx is None
+        with torch.cuda.device(self.dev):
+            self.ctx.use_torch_stream()          # the library's kernels and torch's elementwise / NCCL work share one stream order
+        self.sb = sbins if sbins is not None else self.ctx.bins_create(np.asarray(substrate, dtype=np.float64))
+        self.own_sb = sbins is None
+        self.srcs = [s for s in range(world) if s != rank and self.dec.sends[s][rank]]
+        self.dsts = [d for d in range(world) if d != rank and self.dec.sends[rank][d]]
+        self.cols_for = {d: torch.tensor(self.dec.sends[rank][d], dtype=torch.int64, device=self.dev) for d in self.dsts}
+        self.halo_bytes = 0
+        self.collectives = 0
+        self.partition(adatoms)
+
+    # ---- ownership -------------------------------------------------------------------------------------------
+    def partition(self, adatoms):
+        """(re)assign every adatom to the rank that owns its bin column; every rank computes the same assignment"""
+        torch = self.torch
+        ad = np.asarray(adatoms, dtype=np.float64).reshape(-1, 2)
+        self.n_global = ad.shape[0]
+        owner = self.dec.owner_of(ad[:, 0]) if ad.shape[0] else np.zeros(0, dtype=np.int64)
+        self.gids = [np.nonzero(owner == r)[0].astype(np.int64) for r in range(self.world)]
+        self.n_own = int(len(self.gids[self.rank]))
+        self.gid = torch.from_numpy(self.gids[self.rank]).to(self.dev)
+        self.x = torch.from_numpy(np.ascontiguousarray(ad[self.gids[self.rank]])).to(self.dev)
+        off = self.n_own
+        self.recv_slice = {}
+        for s in self.srcs:
+            self.recv_slice[s] = (off, off + len(self.gids[s]))
+            off += len(self.gids[s])
+        self.n_local = off
+        self.loc4 = torch.empty((self.n_local, 4), dtype=torch.float64, device=self.dev)        # x, y, sx, sy
+        self.loc4[:, 0] = 0.0
+        self.loc4[:, 1] = DUMMY_Y
+        self.loc4[:, 2:] = 0.0
+
+    # ---- halo exchange ---------------------------------------------------------------------------------------
+    def exchange(self, x, s=None):
+        """-> (local positions [n_local, 2], local directions [n_local, 2] or None), contiguous device tensors.
+        Own atoms first; the neighbours' boundary columns behind them (dummies elsewhere)."""
+        torch, dist = self.torch, self.dist
+        w = 4 if s is not None else 2
+        own = torch.cat([x, s], dim=1) if s is not None else x
+        self.loc4[:self.n_own, :w] = own
+        if self.world > 1 and (self.srcs or self.dsts):
+            col = ((x[:, 0] + self.gv.L / 2) / self.gv.bin_size).to(torch.int64).clamp_(0, self.gv.nbins_x - 1)
+            dummy = torch.tensor([0.0, DUMMY_Y, 0.0, 0.0][:w], dtype=torch.float64, device=self.dev)
+            ops, keep = [], []
+            for d in self.dsts:
+                cols = self.dec.sends[self.rank][d]              # one to three columns: plain comparisons (torch.isin sorts)
+                mask = col == cols[0]
+                for cnum in cols[1:]:
+                    mask = mask | (col == cnum)
+                payload = torch.where(mask[:, None], own, dummy).contiguous()
+                keep.append(payload)
+                ops.append(dist.P2POp(dist.isend, payload, d))
+                self.halo_bytes += payload.numel() * 8
+            bufs = {}
+            for src in self.srcs:
+                a, b = self.recv_slice[src]
+                bufs[src] = torch.empty((b - a, w), dtype=torch.float64, device=self.dev)
+                ops.append(dist.P2POp(dist.irecv, bufs[src], src))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                self.collectives += 1
+            for src in self.srcs:
+                a, b = self.recv_slice[src]
+                self.loc4[a:b, :w] = bufs[src]
+        lx = self.loc4[:, 0:2].contiguous()
+        ls = self.loc4[:, 2:4].contiguous() if s is not None else None
+        return lx, ls
+
+    def _allreduce(self, t, op="sum"):
+        if self.world > 1:
+            d = self.dist
+            d.all_reduce(t, op={"sum": d.ReduceOp.SUM, "max": d.ReduceOp.MAX, "min": d.ReduceOp.MIN}[op])
+            self.collectives += 1
+        return t
+
+    # ---- sweeps ----------------------------------------------------------------------------------------------
+    def sweep(self, x=None, forces=True, energies=True, rates=True):
+        """one decomposed sweep of the configuration: dict(F [n_own, 2], energy (0-dim, all ranks), rate_dense, surf_dense)"""
+        torch = self.torch
+        x = self.x if x is None else x
+        lx, _ = self.exchange(x)
+        r = self.ctx.domain_sweep(lx.view(-1), self.n_own, self.sb, forces=forces, energies=energies, rates=rates)
+        out = {}
+        if forces:
+            out["F"] = r["F"].view(-1, 2)
+        if energies:
+            out["energy"] = self._allreduce((0.5 * r["e_aa"].sum() + r["e_as"].sum()).reshape(1))[0]
+        if rates:
+            dense = torch.zeros(self.n_global, dtype=torch.float64, device=self.dev)
+            dsurf = torch.zeros(self.n_global, dtype=torch.float64, device=self.dev)
+            dense.index_copy_(0, self.gid, r["rate"])
+            dsurf.index_copy_(0, self.gid, r["is_surface"].to(torch.float64))
+            both = torch.stack([dense, dsurf])
+            self._allreduce(both)            # slices are disjoint and zero elsewhere: the sum is the assembly, exactly
+            out["rate_dense"], out["surf_dense"] = both[0].contiguous(), both[1].to(torch.uint8).contiguous()
+        return out
+
+    def select(self, u, sw=None):
+        """2DGrowth.py:319-329 on the assembled table: the same sequential-order kernel as on one GPU (bit-exact index)"""
+        sw = self.sweep(forces=False, energies=False, rates=True) if sw is None else sw
+        return self.ctx.select(sw["rate_dense"], sw["surf_dense"], u)
+
+    def gather_positions(self, x=None):
+        """global positions [n_global, 2] on every rank (device)"""
+        torch = self.torch
+        x = self.x if x is None else x
+        g = torch.zeros((self.n_global, 2), dtype=torch.float64, device=self.dev)
+        g.index_copy_(0, self.gid, x)
+        return self._allreduce(g)
+
+    # ---- Relaxation (2DGrowth.py:97-166) over the ranks ------------------------------------------------------------
+    def _line_search(self, xn, sn, scale):
+        """one 20-candidate line search + forces at the winner; -> (xnp, F, maxF, top, bot, miny) with host floats"""
+        torch = self.torch
+        lx, ls = self.exchange(xn, sn)                                              # halo positions AND directions
+        e = self.ctx.domain_line_energies(lx.view(-1), ls.view(-1), self.n_own, self.sb, scale, 20)
+        self._allreduce(e)                                                          # RelaxEnergy of the 20 candidates (:122,153)
+        amin = torch.min(e, dim=0).indices.to(torch.float64)                        # first minimum (:123,155)
+        lxnp = lx + (amin * ls) / 20 / scale                                        # x + a*s/20/scale, own and halo slots (:121,152)
+        r = self.ctx.domain_sweep(lxnp.contiguous().view(-1), self.n_own, self.sb, forces=True, energies=False, rates=False)
+        F = r["F"].view(-1, 2)
+        xnp = lxnp[:self.n_own]
+        big = torch.finfo(torch.float64).max
+        if self.n_own:
+            part = torch.stack([(F * F).sum(dim=1).max(), (xnp * (xnp - xn)).sum(), (xn * xn).sum(), -xnp[:, 1].min()])
+        else:
+            part = torch.tensor([0.0, 0.0, 0.0, -big], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            allp = [torch.empty_like(part) for _ in range(self.world)]
+            self.dist.all_gather(allp, part)
+            self.collectives += 1
+            allp = torch.stack(allp)
+        else:
+            allp = part[None]
+        red = torch.stack([allp[:, 0].max(), allp[:, 1].sum(), allp[:, 2].sum(), -allp[:, 3].max()]).cpu()       # the ONE host sync of a line search
+        return xnp, F, float(red[0]), float(red[1]), float(red[2]), float(red[3])
+
+    def relax(self, scale0=16, threshold0=1e-4, max_line_searches=0):
+        """the reference's Relaxation with its restart rules, host-driven, every sum reduced over the ranks -> dict(stats)"""
+        x0 = self.x.clone()
+        scale, threshold = int(scale0), float(threshold0)
+        ls_count = restarts = 0
+        status = 0
+        maxF = 0.0
+        xnp = x0
+        while True:
+            if scale > 1024:                                                        # :111-113
+                scale, threshold = 16, threshold * 10
+            xn = x0
+            sn = self.sweep(xn, forces=True, energies=False, rates=False)["F"].clone()      # dx0, :120,125
+            xnp, F, maxF, top, bot, miny = self._line_search(xn, sn, scale)         # :121-129
+            ls_count += 1
+            lastmaxF = maxF
+            restart = False
+            while maxF > threshold:                                                 # :131
+                if max_line_searches > 0 and ls_count >= max_line_searches:
+                    status = -6
+                    break
+                if miny > self.gv.Dmax:                                             # :137-140
+                    restart = True
+                    break
+                beta = top / bot                                                    # :143-145
+                sn = F + beta * sn                                                  # :147
+                xn = xnp                                                            # :149
+                xnp, F, maxF, top, bot, miny = self._line_search(xn, sn, scale)     # :152-160
+                ls_count += 1
+                if abs(lastmaxF - maxF) < 1e-8:                                     # :162-164
+                    restart = True
+                    break
+                lastmaxF = maxF
+            if status != 0 or not restart:
+                break
+            restarts += 1
+            scale *= 2
+        self.x = xnp.contiguous().clone()
+        self.ctx.put_all_in_box(self.x.view(-1))                                    # :166
+        return {"line_searches": ls_count, "restarts": restarts, "maxF": maxF, "status": status, "final_scale": scale,
+                "final_threshold": threshold}
+
+    # ---- one KMC event (2DGrowth.py:317-329) ----------------------------------------------------------------------
+    def event(self, u0, u1, max_line_searches=0):
+        """rate table -> selection -> placement on the full state (every rank, identically: the kernels of the single-GPU
+        event chain), then the decomposed relaxation."""
+        g = self.gather_positions().contiguous()
+        self.ctx.state_set(g.view(-1))
+        kind, hk, rtot = self.ctx.event_place(self.sb, u0, u1)
+        self.partition(self.ctx.state_get())
+        st = self.relax(16, 1e-4, max_line_searches)
+        st.update(kind=kind, hop_k=hk, rtot=rtot)
+        return st
+
+    def close(self):
+        if self.own_sb:
+            self.sb.close()
+        if self.own_ctx:
+            self.ctx.close()

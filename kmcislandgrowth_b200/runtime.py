@@ -359,6 +359,28 @@ class Context(object):
     def hop_place(self, sbins, k, u):
         check(self.lib.kmc_hop_place(self.handle, sbins.handle, int(k), float(u)))
 
+    # ---- spatial domain decomposition (local configuration = own atoms first, then halo copies)
+    def domain_sweep(self, xy, n_own, sbins, forces=True, energies=True, rates=True):
+        """-> dict(F[2*n_own], e_aa[n_own], e_as[n_own], rate[n_own], is_surface[n_own]) of the own atoms (one cell build)"""
+        k, p, mem = _in(xy)
+        n = _count(k) // 2
+        o = _Out(k)
+        out = {"F": o.new((2 * n_own,)) if forces else None,
+               "e_aa": o.new((n_own,)) if energies else None, "e_as": o.new((n_own,)) if energies else None,
+               "rate": o.new((n_own,)) if rates else None, "is_surface": o.new((n_own,), np.uint8) if rates else None}
+        check(self.lib.kmc_domain_sweep(self.handle, p, n, int(n_own), sbins.handle, _ptr(out["F"]), _ptr(out["e_aa"]), _ptr(out["e_as"]),
+                                        _ptr(out["rate"]), _ptr(out["is_surface"]), mem))
+        return out
+
+    def domain_line_energies(self, xy, direction, n_own, sbins, scale=16, K=20):
+        """this rank's share of the K candidate energies (all-reduce over the ranks gives RelaxEnergy of every candidate)"""
+        k, p, mem = _in(xy)
+        kd, pd, _ = _in(direction)
+        n = _count(k) // 2
+        out = _Out(k).new((K,))
+        check(self.lib.kmc_domain_line_energies(self.handle, p, pd, n, int(n_own), int(scale), int(K), sbins.handle, _ptr(out), mem))
+        return out
+
     def fp64_peak(self, repeats=5):
         """measured non-tensor FP64 FMA rate of the device -> (TFLOP/s, ms of the best run)"""
         tf, ms = C.c_double(0), C.c_double(0)
@@ -379,6 +401,12 @@ class Context(object):
     def event_enqueue(self, sbins, u0, u1, max_line_searches=0):
         """queue one KMC event on the context's stream; event_finish() waits for it and returns its outcome"""
         check(self.lib.kmc_event_enqueue(self.handle, sbins.handle, float(u0), float(u1), int(max_line_searches)))
+
+    def event_place(self, sbins, u0, u1):
+        """rate table -> selection -> placement, no relaxation -> (kind, hop_k, Rtot)"""
+        kind, hk, rtot = C.c_int32(-1), C.c_int64(-1), C.c_double(0)
+        check(self.lib.kmc_event_place(self.handle, sbins.handle, float(u0), float(u1), C.byref(kind), C.byref(hk), C.byref(rtot)))
+        return kind.value, hk.value, rtot.value
 
     def event_ready(self):
         """True when the enqueued event has completed on the device (event_finish will not block)"""

@@ -1,0 +1,3 @@
+#!/bin/bash
+export KMC_STRESS_WORKLOAD=cfg5_4096x4096 KMC_STRESS_PRERELAX=20000
+timeout 120 python scripts/stress_events.py 1 dbg13 2>&1 | grep -v "^  File\|^    " | tail -4 | cut -c1-2500

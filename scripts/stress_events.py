@@ -7,16 +7,24 @@ import torch
 flags = set(sys.argv[2:])
 if "nofast" in flags:
     os.environ["KMC_DEBUG_E"] = "9"
+for f in flags:
+    if f.startswith("dbg"):
+        os.environ["KMC_DEBUG_E"] = f[3:]
 from kmcislandgrowth_b200 import Growth, runtime, workloads
 reps = int(sys.argv[1])
-gv, sub, ad0 = workloads.make("cfg2_256x256_10k")
+name = os.environ.get("KMC_STRESS_WORKLOAD", "cfg2_256x256_10k")
+if os.environ.get("KMC_STRESS_N"):
+    W_, Hs_, Ha_, n_, seed_, aa_ = workloads.CONFIGS[name]
+    workloads.CONFIGS[name] = (W_, Hs_, Ha_, int(os.environ["KMC_STRESS_N"]), seed_, aa_)
+gv, sub, ad0 = workloads.make(name)
 sim = Growth.Simulation(adatoms=ad0, substrate=sub, device=0, params=runtime.params_from(gv))
 ctx = sim.ctx
 if "ownstream" not in flags:
     ctx.use_torch_stream()
 if "hostmode" in flags:
     sim.set_modes(event_mode=0)
-st, total = workloads.bench_prerelax(ctx, sim.sbins)
+st, total = workloads.bench_prerelax(ctx, sim.sbins, int(os.environ.get("KMC_STRESS_PRERELAX", "200000")))
+print("prerelax", total, int(st.status), flush=True)
 state0 = sim.adatoms.copy()
 us = workloads.bench_uniforms(64)
 flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
@@ -31,7 +39,9 @@ for r in range(reps):
         for s in range(23):
             if "noflush" not in flags:
                 flush.zero_()
-            rec = sim.step(us[s, 0], us[s, 1], 0)
+            rec = sim.step(us[s, 0], us[s, 1], int(os.environ.get("KMC_STRESS_CAP", "0")))
+            if os.environ.get("KMC_STRESS_VERBOSE"):
+                print(s, rec, flush=True)
             sig.append((rec["kind"], rec["hop_k"], rec["line_searches"], rec["restarts"]))
     except Exception as e:
         print("FAILED rep %d step %d after %.1fs: %s" % (r, len(sig), time.perf_counter() - t0, str(e)[:200]), flush=True)

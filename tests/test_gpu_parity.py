@@ -823,3 +823,48 @@ def test_local_relaxation_matches_reference_semantics():
         assert len(stats) == 2 and int(stats[1].line_searches) == int(st2.line_searches)
     assert int(stats[0].line_searches) == int(st1.line_searches)
     assert got.size == allx.size and float(np.max(np.abs(got - allx))) < 1e-6
+
+
+def test_device_domain_world1_matches_the_oracle():
+    """domain.DeviceDomain (the device-resident decomposition of configs[4]) with one rank, config-5 geometry scaled down:
+    sweeps against the oracle, the host-driven decomposed relaxation against the persistent kernel, one event."""
+    import torch
+    from kmcislandgrowth_b200 import domain, runtime, workloads
+    gv = workloads.constants_for(512, 64, 10, aa_mode=1, hop_index_mode=1, deposit_mode=1)
+    sub = workloads.substrate(gv)
+    ad = workloads.film(gv, 1100, 5)
+    o = _oracle_for(gv)
+    osb = o.PutInBins(sub)
+    dd = domain.DeviceDomain(gv, sub, ad, 0, 1, 0)
+    sw = dd.sweep()
+    Fo = (o.AdatomAdatomForces(ad) + o.AdatomSubstrateForces(ad, osb)).reshape(-1, 2)
+    assert np.max(np.abs(sw["F"].cpu().numpy() - Fo)) < 1e-9 * np.max(np.abs(Fo))
+    eo = o.RelaxEnergy((ad, osb))
+    assert abs(float(sw["energy"]) - eo) < 1e-10 * abs(eo)
+    rate_o, surf_o, du_o = o.HoppingRatesDense(ad, osb)
+    assert np.array_equal(sw["surf_dense"].cpu().numpy().astype(bool), surf_o)
+    assert np.allclose(sw["rate_dense"].cpu().numpy(), rate_o, rtol=1e-8)
+    k, dense, rtot = dd.select(0.4321, sw)
+    assert (k, dense) == tuple(o.Select(rate_o, 0.4321)[:2])
+    # decomposed line searches: candidate energies against the oracle, then a capped relaxation against k_relax2
+    F = sw["F"].contiguous()
+    lx, ls = dd.exchange(dd.x, F)
+    e = dd.ctx.domain_line_energies(lx.view(-1), ls.view(-1), dd.n_own, dd.sb, 16, 20).cpu().numpy()
+    for a in (0, 7, 19):
+        cand = ad + a * F.cpu().numpy().reshape(-1) / 20 / 16
+        ea = o.RelaxEnergy((cand, osb))
+        assert abs(e[a] - ea) < 1e-10 * abs(ea), a
+    e19 = dd.ctx.domain_line_energies(lx.view(-1), ls.view(-1), dd.n_own, dd.sb, 16, 19).cpu().numpy()      # K != 20: batched path
+    assert np.max(np.abs(e19 - e[:19])) < 1e-9 * np.max(np.abs(e))
+    st = dd.relax(16, 1e-4, 12)
+    ref = runtime.Context(runtime.params_from(gv), 0)
+    rsb = ref.bins_create(sub)
+    ref.state_set(ad)
+    st2 = ref.relax(rsb, 16, 1e-4, 12)
+    assert st["line_searches"] == int(st2.line_searches) == 12
+    assert np.max(np.abs(dd.gather_positions().cpu().numpy().reshape(-1) - ref.state_get())) < 1e-8
+    ev = dd.event(0.37, 0.31, 8)                    # one event on the decomposed state (placement on the gathered state)
+    assert ev["kind"] in (0, 1) and dd.n_global == 1100 + (1 - ev["kind"]) and ev["line_searches"] == 8
+
+    rsb.close(); ref.close(); dd.close()
+    torch.cuda.synchronize()
