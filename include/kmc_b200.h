@@ -226,7 +226,7 @@ int kmc_domain_line_energies(KmcCtx* ctx, const double* xy, const double* dir, i
 /* Measurement helpers (bench.py).  kmc_fp64_peak: non-tensor FP64 FMA rate of the device in TFLOP/s (register-resident
  * DFMA chains at full occupancy, best of `repeats` runs, CUDA events) -- the denominator of the pair kernels' FP-pipe
  * roofline.  kmc_relax_diag: counters of the context's last relaxation: out[0] re-sorts of the
- * cell-sorted state, out[1] movers summed over its line searches, out[2] work items, out[3] reserved. */
+ * cell-sorted state, out[1] movers summed over its line searches, out[2] work items; out[3] = rate-table entries recomputed by the last kmc_rates_update / thresholded kmc_event. */
 int kmc_fp64_peak(KmcCtx* ctx, int32_t repeats, double* tflops_out, double* ms_out);
 int kmc_relax_diag(KmcCtx* ctx, int64_t out[4]);
 

@@ -80,6 +80,8 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
     TRY(slot(c, S_KEY, (size_t)n, &R.key));
     TRY(slot(c, S_PERM, (size_t)n, &R.perm));
     TRY(slot(c, S_CHUNKS, (size_t)c->dp.ncell * R2_PARTS + 2, &R.chunks));
+    TRY(slot(c, S_COLR, (size_t)c->dp.nbx, &R.colr));
+    TRY(slot(c, S_BX, (size_t)R2_MAXBLK, &R.tile_tot));
     TRY(slot(c, S_ITEMS, c->item_cap, &R.items));
     R.item_cap = (int)c->item_cap;
     TRY(slot(c, S_MOVERS, (size_t)n, &R.movers));
@@ -190,6 +192,7 @@ int kmc_relax2_persistent(KmcCtx* c, const KmcBins* sb, int32_t scale0, double t
 
 extern "C" int kmc_relax_diag(KmcCtx* c, int64_t out[4]) {
     if (!c || !out) return kmc_fail(KMC_E_ARG, "NULL argument");
-    for (int k = 0; k < 4; ++k) out[k] = c->diag[k];
+    for (int k = 0; k < 3; ++k) out[k] = c->diag[k];
+    out[3] = c->rc_last;
     return 0;
 }

@@ -51,6 +51,8 @@ constexpr int R2_FB = KMC_R2_FB;       // neighbours fetched and evaluated per b
 constexpr int R2_CHUNK = KMC_R2_CHUNK;        // pairs per work item
 constexpr int R2_WI = 12;          // work items of a warp cached in shared memory between rebuilds
 constexpr int R2_PARTS = 8;         // per home cell: adatom columns 0..3, substrate columns 0..3
+constexpr int R2_TALL = 16384;      // cell grids above this size (configs[4]: 1.6 M cells, a few thousand occupied) take the rebuild
+                                    // path whose scans run on the whole grid and whose per-cell work visits occupied rows only
 
 struct WorkItem {
     int hb, nh;            // home atoms: slots [hb, hb+nh)
@@ -82,6 +84,8 @@ struct Relax2Args {
     int* cursor;            // [ncell+2]
     int* key;               // [n] scratch: cell of source element
     int* perm;              // [n] scratch: source element of a slot
+    int2* colr;             // tall grids only (ncell2 > R2_TALL): lowest / highest occupied cell row of every column
+    int* tile_tot;          // tall grids only: per-block totals of the grid-wide scans
     int* chunks;            // [ncell*R2_PARTS + 1] items per (cell, part), then their exclusive scan
     WorkItem* items;        // work list
     int* n_items;
@@ -244,13 +248,77 @@ __device__ __forceinline__ Ranges partner_ranges(const DevParams& P, const int* 
     return r;
 }
 
-// ---- rebuild of the sorted state from `n` source elements (7 barriers) ---------------------------
+// In-place inclusive scan of a[1..m] over the WHOLE grid (a[0] is left alone), optional mirror copy: every block scans its
+// tile and publishes the tile total, one grid barrier, every block adds the totals of the tiles before it.  (The one-block
+// scan of the small-grid path walks 1.6 M cells with 512 threads on configs[4]: milliseconds per rebuild.)  A real function
+// (rare path, plain arguments): it must not bloat the persistent kernel, whose line-search body has to stay inlined.
+// `epoch` is the caller's barrier epoch: the function executes ONE grid barrier, the caller increments its counter.
+// Returns true when the watchdog fired.
+__device__ __noinline__ bool relax2_scan_tall(int* a, int m, int* mirror, int* total_out, int* tile_tot, int* s_scan,
+                                              unsigned int* bar, int* abortw, unsigned int epoch) {
+    const int T = blockDim.x, t = threadIdx.x, nb = gridDim.x;
+    const int tile = (m + nb - 1) / nb;
+    const int tlo = 1 + blockIdx.x * tile, thi = min(tlo + tile, m + 1);
+    const int per = (tile + T - 1) / T;
+    const int lo = tlo + t * per, hi = min(lo + per, thi);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    s_scan[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {
+        int v = (t >= off) ? s_scan[t - off] : 0;
+        __syncthreads();
+        s_scan[t] += v;
+        __syncthreads();
+    }
+    const int before = s_scan[t] - sum;
+    if (t == T - 1) tile_tot[blockIdx.x] = s_scan[t];
+    bool dead = false;
+    __syncthreads();
+    if (t == 0) {
+        const unsigned int target = (epoch + 1u) * gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
+        unsigned int v;
+        const unsigned long long t0 = gtimer();
+        unsigned int spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if ((++spins & 1023u) == 0) {
+                if (*(volatile int*)abortw != 0) { dead = true; break; }
+                if (gtimer() - t0 > R2_SPIN_NS) { atomicCAS(abortw, 0, 1); dead = true; break; }
+            }
+        } while ((int)(v - target) < 0);
+    }
+    if (__syncthreads_or(dead)) return true;
+    int offset = 0;
+    for (int b = t; b < (int)blockIdx.x; b += T) offset += tile_tot[b];
+    s_scan[t] = offset;
+    __syncthreads();
+    for (int off = T >> 1; off > 0; off >>= 1) {
+        if (t < off) s_scan[t] += s_scan[t + off];
+        __syncthreads();
+    }
+    int run = s_scan[0] + before;
+    __syncthreads();
+    for (int i = lo; i < hi; ++i) { run += a[i]; a[i] = run; if (mirror) mirror[i] = run; }
+    if (mirror && blockIdx.x == 0 && t == 0) mirror[0] = a[0];
+    if (total_out && blockIdx.x == nb - 1 && t == 0) {
+        int tot = 0;
+        for (int b = 0; b < nb; ++b) tot += tile_tot[b];
+        *total_out = tot;
+    }
+    return false;
+}
+
+// ---- rebuild of the sorted state from `n` source elements (7 barriers; 9 on tall grids) ----------------------
 // src_s / src_oidx may be null (direction 0 / identity index).
 __device__ __forceinline__ bool relax2_rebuild(const Relax2Args& R, const double2* src_pos, const double2* src_s, const int* src_oidx,
                                                double2* dst_pos, double2* dst_s, int* dst_oidx, unsigned int& epoch, Relax2Smem& S, int nA) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const DevParams& P = R.P;
+    const bool tall = R.ncell2 > R2_TALL && gridDim.x > 1;
     for (int c = gtid; c < R.ncell2; c += gthreads) R.start[c] = 0;
+    if (tall) for (int c = gtid; c < P.nbx; c += gthreads) R.colr[c] = make_int2(0x7fffffff, -1);
     if (relax2_barrier(R, epoch)) return true;
     for (int k = gtid; k < nA; k += gthreads) {
         int nx, ny;
@@ -258,9 +326,13 @@ __device__ __forceinline__ bool relax2_rebuild(const Relax2Args& R, const double
         const int c = flat_cell(P, nx, ny);
         R.key[k] = c;
         atomicAdd(&R.start[1 + c], 1);
+        if (tall && c < P.ncell) { atomicMin(&R.colr[nx].x, ny); atomicMax(&R.colr[nx].y, ny); }
     }
     if (relax2_barrier(R, epoch)) return true;
-    if (blockIdx.x == 0) {
+    if (tall) {
+        if (relax2_scan_tall(R.start, R.ncell2 - 1, R.cursor, nullptr, R.tile_tot, S.u.e.scan, R.barrier, R.abort, epoch)) return true;
+        ++epoch;
+    } else if (blockIdx.x == 0) {
         const int T = blockDim.x, t = threadIdx.x;
         const int m = R.ncell2 - 1;
         const int per = (m + T - 1) / T;
@@ -290,7 +362,39 @@ __device__ __forceinline__ bool relax2_rebuild(const Relax2Args& R, const double
     // One WARP per cell: cells of up to 32 atoms are ranked with shuffles (three dependent fetches in all); the
     // rest of the per-cell work below is done by lane 0.
     const int gwarp_ = gtid >> 5, nwarps_ = gthreads >> 5, lane_ = threadIdx.x & 31;
-    for (int c = gwarp_; c < R.ncell2 - 1; c += nwarps_) {
+    // cells visited by this warp: every nwarps-th cell of the grid, or -- tall grid -- the occupied rows of every nwarps-th
+    // column plus the overflow cell (the counters of the many empty cells are zeroed by a streaming pass: every cell has
+    // exactly one writer).  ONE instance of the per-cell body.
+    if (tall)
+        for (int c = gtid; c < P.ncell; c += gthreads)
+            if (R.start[c + 1] == R.start[c]) R.cursor[1 + c] = 0;
+    int it_col = gwarp_, it_row = 0, it_hi = -1, it_c = gwarp_ - nwarps_;
+    bool it_over = false;
+    for (;;) {
+        int c;
+        if (!tall) {
+            it_c += nwarps_;
+            if (it_c >= R.ncell2 - 1) break;
+            c = it_c;
+        } else if (it_row <= it_hi) {
+            c = (it_col - nwarps_) * P.nby + it_row;
+            ++it_row;
+        } else {
+            bool found = false;
+            for (; it_col < P.nbx; it_col += nwarps_) {
+                const int2 r = R.colr[it_col];
+                if (r.x <= r.y) { it_row = r.x; it_hi = r.y; found = true; break; }
+            }
+            if (found) {
+                c = it_col * P.nby + it_row;
+                ++it_row;
+                it_col += nwarps_;
+            } else {
+                if (it_over || gwarp_ != 0) break;
+                it_over = true;
+                c = P.ncell;                  // the overflow cell (atoms outside the grid)
+            }
+        }
         const int lo = R.start[c], hi = R.start[c + 1];
         const int m = hi - lo;
         if (m == 0) {               // empty cell: no work items (the counters still have to be defined)
@@ -371,10 +475,13 @@ __device__ __forceinline__ bool relax2_rebuild(const Relax2Args& R, const double
             }
             R.cursor[1 + c] = tot;          // items of this home cell (the scatter cursor is free again)
         }
-    }
+        }
     if (gtid == 0) R.cursor[0] = 0;
     if (relax2_barrier(R, epoch)) return true;
-    if (blockIdx.x == 0) {      // inclusive scan of the per-cell item counts cursor[1..ncell]
+    if (tall) {
+        if (relax2_scan_tall(R.cursor, P.ncell, nullptr, R.n_items, R.tile_tot, S.u.e.scan, R.barrier, R.abort, epoch)) return true;
+        ++epoch;
+    } else if (blockIdx.x == 0) {      // inclusive scan of the per-cell item counts cursor[1..ncell]
         const int T = blockDim.x, t = threadIdx.x;
         const int m = P.ncell;
         const int per = (m + T - 1) / T;

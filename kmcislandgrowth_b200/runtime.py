@@ -388,10 +388,11 @@ class Context(object):
         return tf.value, ms.value
 
     def relax_diag(self):
-        """counters of the last relaxation: dict(resorts, movers, work_items)"""
+        """counters of the last relaxation: dict(resorts, movers, work_items), plus rates_recomputed = the number of
+        rate-table entries the last kmc_rates_update / thresholded kmc_event recomputed"""
         out = (C.c_int64 * 4)()
         check(self.lib.kmc_relax_diag(self.handle, out))
-        return {"resorts": int(out[0]), "movers": int(out[1]), "work_items": int(out[2])}
+        return {"resorts": int(out[0]), "movers": int(out[1]), "work_items": int(out[2]), "rates_recomputed": int(out[3])}
 
     def set_event_mode(self, mode):
         """1 (default): a KMC event is queued as one chain of kernels with a single host synchronisation;
