@@ -408,7 +408,7 @@ def sharded_configs(args, world, rank, progress):
     sweep64 = domain_cfg5 = None
     try:
         import bench_sweep64
-        sweep64 = bench_sweep64.run(nev=args.sweep_events, width=16, tag="bench")
+        sweep64 = bench_sweep64.run(nev=args.sweep_events, width=8, tag="bench")
         progress("sweep64 done")
     except Exception as e:                      # a failure here must not take the headline line down
         sweep64 = {"error": repr(e)[:300]}

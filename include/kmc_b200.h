@@ -226,9 +226,20 @@ int kmc_domain_line_energies(KmcCtx* ctx, const double* xy, const double* dir, i
 /* Measurement helpers (bench.py).  kmc_fp64_peak: non-tensor FP64 FMA rate of the device in TFLOP/s (register-resident
  * DFMA chains at full occupancy, best of `repeats` runs, CUDA events) -- the denominator of the pair kernels' FP-pipe
  * roofline.  kmc_relax_diag: counters of the context's last relaxation: out[0] re-sorts of the
- * cell-sorted state, out[1] movers summed over its line searches, out[2] work items; out[3] = rate-table entries recomputed by the last kmc_rates_update / thresholded kmc_event. */
+ * cell-sorted state, out[1] movers summed over its line searches, out[2] work items; out[3] = rate-table entries
+ * recomputed by the last kmc_rates_update / thresholded kmc_event. */
 int kmc_fp64_peak(KmcCtx* ctx, int32_t repeats, double* tflops_out, double* ms_out);
 int kmc_relax_diag(KmcCtx* ctx, int64_t out[4]);
+
+/* The persistent adatom cell list of the trajectory state (replaces the reference's PutInBins of the whole adatom array
+ * per neighbour query, Bins.py:91): kmc_rates_update and the thresholded kmc_event edit it in place -- only atoms whose
+ * cell id changed, the atom HopAtom deleted (2DGrowth.py:241) and appended atoms (:93,:255) are re-filed -- and fall
+ * back to a rebuild beyond 64 edits.  kmc_cells_stats: out[0] full builds, out[1] in-place updates, out[2] edits of the
+ * last update (atoms, after a full build), out[3] result of the last kmc_cells_check.  kmc_cells_check brings the list
+ * up to date, builds the same list from scratch and returns the number of words (starts, indices, position bit
+ * patterns) in which the two differ: 0 by construction (tests). */
+int kmc_cells_stats(KmcCtx* ctx, int64_t out[4]);
+int kmc_cells_check(KmcCtx* ctx, int64_t* differing_words);
 
 #ifdef __cplusplus
 }

@@ -122,8 +122,7 @@ static int check_params(const KmcParams* p) {
 
 // ------------------------------------------------------------------------------------ cell lists
 // B configurations of n atoms each (d_xy[b*n+i]).
-static int build_cells(KmcCtx* c, const double2* d_xy, int n, int B, int* cell_of, int* start, int* cursor, int* sidx,
-                       double2* sxy) {
+int kmc_build_cells(KmcCtx* c, const double2* d_xy, int n, int B, int* cell_of, int* start, int* cursor, int* sidx, double2* sxy) {
     const int ncell2 = c->dp.ncell + 2;
     TRY(kmc_zero_async(c, start, sizeof(int) * (size_t)ncell2 * B));
     if (n > 0) {
@@ -160,7 +159,7 @@ int kmc_scratch_cells(KmcCtx* c, const double2* d_xy, int n, int B, CellView* ou
     TRY(slot(c, S_CURSOR, (size_t)ncell2 * B, &cursor));
     TRY(slot(c, S_SIDX, (size_t)n * B, &sidx));
     TRY(slot(c, S_SXY, (size_t)n * B, &sxy));
-    TRY(build_cells(c, d_xy, n, B, cell_of, start, cursor, sidx, sxy));
+    TRY(kmc_build_cells(c, d_xy, n, B, cell_of, start, cursor, sidx, sxy));
     out->start = start; out->sxy = sxy; out->sidx = sidx; out->n = n;
     return 0;
 }
@@ -303,6 +302,7 @@ static int rc_reserve(KmcCtx* c, int64_t n) {
 // the cached tables follow the index changes of the trajectory state: HopAtom deletes entry k and appends the moved atom
 // (2DGrowth.py:241,255), DepositAdatom appends (:93).  A new atom has no cached entry (NaN reference position).
 int kmc_rc_on_remove(KmcCtx* c, int k) {
+    kmc_cells_on_remove(c, k);
     if (!c->rc_valid) return 0;
     const int n = (int)c->rc_n;
     if (c->rc_npending >= RC_PENDING) { c->rc_valid = false; return 0; }
@@ -325,6 +325,7 @@ int kmc_rc_on_remove(KmcCtx* c, int k) {
     return 0;
 }
 int kmc_rc_on_append(KmcCtx* c) {
+    kmc_cells_on_append(c);
     if (!c->rc_valid) return 0;
     TRY(rc_reserve(c, c->rc_n + 1));
     CK(cudaMemsetAsync(c->rc_xy + c->rc_n, 0xFF, sizeof(double2), c->stream));      // all-ones bit pattern == NaN: "no cached entry"
@@ -357,7 +358,7 @@ int kmc_rates_update_impl(KmcCtx* c, const KmcBins* sb, double threshold, int64_
     LAUNCH(c, "rates_mark", k_rates_mark, cdiv(std::max(n, c->rc_npending), 256), 256, c->dp, (const double2*)c->st_xy, (const double2*)c->rc_xy, n,
            threshold * threshold, (const double2*)c->rc_pending, c->rc_npending, dirty_cell, self_dirty);
     CellView ad;
-    TRY(kmc_scratch_cells(c, (const double2*)c->st_xy, n, 1, &ad));
+    TRY(kmc_cells_update(c, &ad));          // the persistent list, edited in place (kmc_cells.cu)
     const int G = pick_group(n);
     const unsigned grid = cdiv((size_t)n * G, 256);
     CellView sub = view_of(sb);
@@ -628,7 +629,7 @@ int kmc_bins_create(KmcCtx* c, const double* xy, int64_t n, int mem, KmcBins** o
         if (n > 0)
             CK(cudaMemcpyAsync(b->xy, xy, sizeof(double2) * (size_t)n, mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
         TRY(slot(c, S_CURSOR, (size_t)b->ncell2, &cursor));
-        TRY(build_cells(c, b->xy, (int)n, 1, b->cell_of, b->start, cursor, b->sidx, b->sxy));
+        TRY(kmc_build_cells(c, b->xy, (int)n, 1, b->cell_of, b->start, cursor, b->sidx, b->sxy));
         if (mem == KMC_HOST) CK(cudaStreamSynchronize(c->stream));
         return 0;
     };
@@ -938,6 +939,7 @@ int kmc_state_set(KmcCtx* c, const double* xy, int64_t n, int mem) {
         CK(cudaMemcpyAsync(c->st_xy, xy, sizeof(double) * 2 * (size_t)n, mem == KMC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     c->st_n = n;
     c->rc_valid = false;            // an uploaded state has no history: the next rate table is a full sweep
+    c->pl_valid = false;
     if (mem == KMC_HOST) CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

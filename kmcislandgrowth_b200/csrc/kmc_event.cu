@@ -342,6 +342,7 @@ int collect_placement(KmcCtx* c, int32_t* kind_out, int64_t* hop_k_out, double* 
     if (M->status != 0) return kmc_fail(M->status, "event placement failed");
     c->st_n = M->n_new;
     c->rc_valid = false;           // the placement bypassed the incremental rate cache's bookkeeping
+    c->pl_valid = false;
     return 0;
 }
 

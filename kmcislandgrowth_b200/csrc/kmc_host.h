@@ -101,6 +101,14 @@ struct KmcCtx {
     int rc_npending = 0;
     int64_t rc_cap = 0, rc_n = 0, rc_last = 0;
     bool rc_valid = false;
+    // persistent adatom cell list of the trajectory state (kmc_cells.cu): edited in place by the incremental rate table
+    bool pl_valid = false;
+    int pl_cur = 0;                 // which of the two buffer sets holds the list
+    int64_t pl_n = 0;               // atoms filed in it
+    int pl_removed = -1;            // index HopAtom deleted since the last update (-1: none)
+    int pl_appended = 0;            // atoms appended since the last update
+    uintptr_t pl_sig = 0;           // signature of the buffer addresses (a grown scratch slot loses its content)
+    int64_t pl_stats[4] = {0, 0, 0, 0};   // full builds, in-place updates, edits of the last update (atoms after a full build), last kmc_cells_check
     int select_mode = 0;            // 0: sequential-order sums up to 65536 atoms, block scan beyond; 1: always sequential; 2: always block scan
     int event_mode = 1;             // 1 (default): the whole event is enqueued without a host round trip; 0: host-stepped placement (cross-check)
     int sm_count = 148;
@@ -133,7 +141,9 @@ enum Slot {
     S_F, S_FAA, S_FAS, S_X0, S_XN, S_XNP, S_SN, S_TMP0, S_TMP1, S_TMP2, S_TMP3,
     S_FLAG, S_MOVERS, S_NMOV, S_LPART, S_FIX, S_AMIN, S_RED, S_SYNC,
     S_POS0, S_POS1, S_SD0, S_SD1, S_OI0, S_OI1, S_KEY, S_PERM, S_CHUNKS, S_ITEMS, S_NBR,
-    S_EVMAIL, S_EVTMP, S_EVRATE, S_EVSURF, S_HALO0, S_HALO1, S_PX, S_BX, S_COLR, S_COUNT
+    S_EVMAIL, S_EVTMP, S_EVRATE, S_EVSURF, S_HALO0, S_HALO1, S_PX, S_BX, S_COLR,
+    S_PL_START0, S_PL_START1, S_PL_SIDX0, S_PL_SIDX1, S_PL_CELL0, S_PL_CELL1, S_PL_SLOT0, S_PL_SLOT1, S_PL_SXY0, S_PL_SXY1, S_PL_EDITS,
+    S_COUNT
 };
 
 int kmc_ensure(KmcCtx* c, DBuf& b, size_t bytes);
@@ -233,6 +243,11 @@ static inline kmc::CellView view_of(const KmcBins* b) {
 // ------------------------------------------------------------------------------------ cross-file entry points
 // kmc_b200.cu
 int kmc_scratch_cells(KmcCtx* c, const double2* d_xy, int n, int B, kmc::CellView* out);
+int kmc_build_cells(KmcCtx* c, const double2* d_xy, int n, int B, int* cell_of, int* start, int* cursor, int* sidx, double2* sxy);
+// kmc_cells.cu
+int kmc_cells_update(KmcCtx* c, kmc::CellView* out);
+void kmc_cells_on_remove(KmcCtx* c, int k);
+void kmc_cells_on_append(KmcCtx* c);
 int kmc_rates_dev(KmcCtx* c, const double2* d_xy, int n, const KmcBins* sb, double* rate, uint8_t* surf, double* du, double* ua, double* ul,
                   int* na, int* ns);
 int kmc_state_reserve(KmcCtx* c, int64_t n);

@@ -394,6 +394,18 @@ class Context(object):
         check(self.lib.kmc_relax_diag(self.handle, out))
         return {"resorts": int(out[0]), "movers": int(out[1]), "work_items": int(out[2]), "rates_recomputed": int(out[3])}
 
+    def cells_stats(self):
+        """persistent adatom cell list: dict(full_builds, in_place_updates, last_edits, last_check)"""
+        out = (C.c_int64 * 4)()
+        check(self.lib.kmc_cells_stats(self.handle, out))
+        return {"full_builds": int(out[0]), "in_place_updates": int(out[1]), "last_edits": int(out[2]), "last_check": int(out[3])}
+
+    def cells_check(self):
+        """words in which the in-place edited cell list differs from a rebuilt one (0 by construction)"""
+        d = C.c_int64(0)
+        check(self.lib.kmc_cells_check(self.handle, C.byref(d)))
+        return int(d.value)
+
     def set_event_mode(self, mode):
         """1 (default): a KMC event is queued as one chain of kernels with a single host synchronisation;
         0: first-generation host-stepped placement (same results, cross-check)"""

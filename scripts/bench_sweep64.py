@@ -15,7 +15,7 @@ import torch.distributed as dist
 from kmcislandgrowth_b200 import replicas
 
 
-def run(nev=30, width=16, threads=1, static=False, tag="timed"):
+def run(nev=30, width=8, threads=1, static=False, tag="timed"):
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     own_group = world > 1 and not dist.is_initialized()
     if own_group:

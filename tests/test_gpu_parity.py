@@ -486,6 +486,74 @@ def test_incremental_rate_table_touches_only_the_neighbourhood():
         ctx.close()
 
 
+def test_persistent_cell_list_is_edited_in_place_and_equals_a_rebuild():
+    """Row n1: the incremental rate table keeps ONE adatom cell list on the context and edits it (kmc_cells.cu) instead of
+    re-binning every adatom (Bins.py:91).  After every kind of change -- one atom carried across cell borders, jitter of
+    all atoms, a hop (np.delete + append, 2DGrowth.py:241,255), a deposition (:93), a relaxation, many movers at once
+    (rebuild fallback) -- the edited list must be word for word the list a rebuild produces (kmc_cells_check == 0), and
+    the small changes must really be in-place updates with a handful of edits."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    gv = workloads.constants_for(128, 16, 16, aa_mode=1, hop_index_mode=1, deposit_mode=1)
+    sub, ad = workloads.substrate(gv), workloads.film(gv, 1500, seed=8, sigma=0.02)
+    ctx = runtime.Context(runtime.params_from(gv), 0)
+    sb = ctx.bins_create(sub)
+    rng = np.random.default_rng(12)
+    try:
+        ctx.set_event_mode(0)                                   # host-stepped placement: the path the incremental table runs on
+        ctx.state_set(ad)
+        ctx.rates_update(sb, 0.0)
+        st = ctx.cells_stats()
+        assert (st["full_builds"], st["in_place_updates"]) == (1, 0)
+        assert ctx.cells_check() == 0
+        x = ad.copy()
+        for step in range(6):                                   # one atom walks through several cells, in both directions
+            k = int(rng.integers(0, 1500))
+            x[2 * k] += float(rng.choice([-1.0, 1.0])) * gv.bin_size * 1.1
+            x[2 * k + 1] += 0.6 * gv.bin_size * (step % 3 - 1)
+            ctx.state_move(x)
+            inc = ctx.rates_update(sb, 0.0)
+            full = ctx.rates(x, sb)
+            assert np.array_equal(inc["rate"], full["rate"]) and np.array_equal(inc["is_surface"], full["is_surface"])
+            st = ctx.cells_stats()
+            assert st["full_builds"] == 1 and 1 <= st["last_edits"] <= 2, st
+            assert ctx.cells_check() == 0
+        y = x + rng.normal(0, 1e-3, x.shape)                    # everybody moves a little: a few atoms near a cell wall change cell
+        ctx.state_move(y)
+        ctx.rates_update(sb, 0.0)
+        assert ctx.cells_check() == 0 and ctx.cells_stats()["full_builds"] == 1
+        n_updates = ctx.cells_stats()["in_place_updates"]
+        # index shifts: HopAtom of a low index (every later atom moves down one slot in the array), a deposition, relaxations
+        cur = ctx.state_get()
+        ctx.hop_place(sb, int(np.argmax(cur[1::2])), 0.4)
+        ctx.relax(sb, 16, 1e-4, 30)
+        inc = ctx.rates_update(sb, 0.0)
+        full = ctx.rates(ctx.state_get(), sb)
+        assert np.array_equal(inc["rate"], full["rate"])
+        assert ctx.cells_check() == 0
+        ctx.deposit_place(sb, 0.7)
+        ctx.relax(sb, 16, 1e-4, 30)
+        ctx.rates_update(sb, 0.0)
+        assert ctx.cells_check() == 0
+        st = ctx.cells_stats()
+        assert st["full_builds"] == 1 and st["in_place_updates"] >= n_updates + 2, st
+        # thresholded events use the same list
+        ctx.set_rate_mode(1, 1e-3)
+        for t in range(4):
+            ctx.event(sb, float(rng.uniform()), float(rng.uniform()), 30)
+            assert ctx.cells_check() == 0
+        assert ctx.cells_stats()["full_builds"] == 1
+        # hundreds of atoms change cell at once: more edits than are applied in place -> one rebuild, same list
+        z = ctx.state_get()
+        z[0::2] += 0.45 * gv.bin_size
+        ctx.state_move(z)
+        ctx.rates_update(sb, 0.0)
+        assert ctx.cells_stats()["full_builds"] == 2
+        assert ctx.cells_check() == 0
+    finally:
+        sb.close()
+        ctx.close()
+
+
 @pytest.mark.parametrize("W,Hs,Ha,n,cap", [(512, 16, 48, 20000, 8), (1024, 16, 96, 80000, 3)])
 def test_relaxation_large_chunks_follow_the_oracle(W, Hs, Ha, n, cap):
     """Films whose per-block chunk exceeds the shared-memory caches of k_relax2 (more than 80 atoms per block: stencil
