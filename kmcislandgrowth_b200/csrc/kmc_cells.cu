@@ -20,6 +20,8 @@
 #include "kmc_host.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 using namespace kmc;
 
@@ -154,13 +156,16 @@ __global__ void k_cells_inverse(int n, const int* __restrict__ sidx, int* __rest
     if (s < n) slot_of[sidx[s]] = s;
 }
 
-// words in which two lists differ (starts, indices, position bits)
+// words in which two lists differ (starts, indices, position bits).  An out-of-grid cell of more than 64 atoms is left
+// unsorted by k_bin_order (nobody's stencil addresses it): its slots are compared as counts only.
 __global__ void k_cells_compare(int n, int ncell2, const int* __restrict__ sa, const int* __restrict__ ia, const double2* __restrict__ pa,
                                 const int* __restrict__ sb, const int* __restrict__ ib, const double2* __restrict__ pb,
                                 unsigned long long* __restrict__ diff) {
     unsigned long long d = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell2; i += gridDim.x * blockDim.x) d += sa[i] != sb[i];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int ovf = sb[ncell2 - 2];
+    const int n_cmp = (sb[ncell2 - 1] - ovf > 64) ? ovf : n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cmp; i += gridDim.x * blockDim.x) {
         d += ia[i] != ib[i];
         d += (__double_as_longlong(pa[i].x) != __double_as_longlong(pb[i].x)) || (__double_as_longlong(pa[i].y) != __double_as_longlong(pb[i].y));
     }
@@ -288,5 +293,20 @@ extern "C" int kmc_cells_check(KmcCtx* c, int64_t* differing_words) {
     TRY(kmc_mail(c, diff, 8));
     *differing_words = (int64_t) * (const unsigned long long*)c->h_mail;
     c->pl_stats[3] = *differing_words;
+    if (*differing_words != 0 && getenv("KMC_CELLS_DEBUG")) {        // diagnostics: the first differing entries
+        const int ncell2 = c->dp.ncell + 2;
+        std::vector<int> sa(ncell2), sb(ncell2), ia(n), ib(n);
+        cudaMemcpy(sa.data(), pl.start, sizeof(int) * ncell2, cudaMemcpyDeviceToHost);
+        cudaMemcpy(sb.data(), ref.start, sizeof(int) * ncell2, cudaMemcpyDeviceToHost);
+        cudaMemcpy(ia.data(), pl.sidx, sizeof(int) * n, cudaMemcpyDeviceToHost);
+        cudaMemcpy(ib.data(), ref.sidx, sizeof(int) * n, cudaMemcpyDeviceToHost);
+        int shown = 0;
+        for (int i = 0; i < ncell2 && shown < 8; ++i)
+            if (sa[i] != sb[i]) { fprintf(stderr, "[cells] start[%d] %d != %d\n", i, sa[i], sb[i]); ++shown; }
+        shown = 0;
+        for (int i = 0; i < n && shown < 12; ++i)
+            if (ia[i] != ib[i]) { fprintf(stderr, "[cells] sidx[%d] %d != %d\n", i, ia[i], ib[i]); ++shown; }
+        fprintf(stderr, "[cells] n %d stats %lld %lld %lld\n", n, (long long)c->pl_stats[0], (long long)c->pl_stats[1], (long long)c->pl_stats[2]);
+    }
     return 0;
 }

@@ -91,6 +91,24 @@ def run(name="cfg5_4096x4096", reps=20, n_events=6, max_ls=150):
         kinds.append(st["kind"])
     sync()
     t_ev = tmax(time.perf_counter() - t0)
+    # ---- the same events on ONE GPU through the persistent relaxation kernel (rank 0; what the decomposition competes with)
+    single = None
+    if rank == 0:
+        one = runtime.Context(runtime.params_from(gv), local)
+        one.state_set(ad)
+        one.event(dd.sb, us[0, 0], us[0, 1], max_ls)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        nls1, kinds1 = 0, []
+        for s in range(n_events):
+            kind, _, _, st1 = one.event(dd.sb, us[1 + s, 0], us[1 + s, 1], max_ls)
+            nls1 += int(st1.line_searches)
+            kinds1.append(int(kind))
+        torch.cuda.synchronize()
+        dt1 = time.perf_counter() - t1
+        single = {"events_per_s": n_events / dt1, "us_per_line_search": dt1 / max(nls1, 1) * 1e6, "line_searches": nls1,
+                  "same_event_kinds_and_line_searches": kinds1 == [int(k) for k in kinds] and nls1 == nls}
+        one.close()
     out = None
     if rank == 0:
         out = {"workload": name, "n_gpus": world, "ms_per_sweep": t_sweep * 1e3, "sweeps_per_s": 1.0 / t_sweep,
@@ -99,6 +117,7 @@ def run(name="cfg5_4096x4096", reps=20, n_events=6, max_ls=150):
                "events_per_s": n_events / t_ev, "events": n_events, "line_search_cap_per_event": max_ls,
                "us_per_line_search": t_ev / max(nls, 1) * 1e6, "line_searches": nls, "event_kinds": kinds,
                "owned_adatoms_rank0": dd.n_own, "local_atoms_rank0": dd.n_local, "agreement_with_single_domain": check,
+               "single_gpu_persistent_kernel": single,
                "limiting_step": "per line search: 1 NCCL send/recv group (halo x and s), 1 all-reduce (20 candidate energies), 1 all-gather "
                                 "(max|F|^2, top, bot, min y) and one host read of 4 doubles; the messages are KBs, the cost is their latency"}
     dd.close()
