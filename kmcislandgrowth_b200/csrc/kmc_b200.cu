@@ -233,7 +233,9 @@ static int line_energies_dev(KmcCtx* c, const double2* d_x, const double2* d_s, 
     TRY(slot(c, S_FIX, (size_t)n * KC, &A.fix));
     A.e_out = d_e; A.amin_out = d_amin;
     A.colrange = nullptr;
-    if (c->dp.nby > 64 && ad.start == (const int*)c->slots[S_START].p) {      // tall grid, scratch cell list of this call: occupied rows per column
+    // sparse tall grid (configs[4]: 198 cells per adatom) and the scratch cell list of this call: occupied rows per column.  The
+    // home cells are then dealt out by COLUMN, which starves the grid on a dense film (86 columns for 1184 blocks on configs[1]).
+    if (c->dp.nby > 64 && (size_t)c->dp.ncell > 16 * (size_t)n && ad.start == (const int*)c->slots[S_START].p) {
         int2* cr;
         TRY(slot(c, S_COLR, (size_t)c->dp.nbx, &cr));
         LAUNCH(c, "line_mark", k_colrange_init, cdiv(c->dp.nbx, 256), 256, cr, c->dp.nbx);

@@ -254,6 +254,71 @@ __device__ __forceinline__ void acc_force(const DevParams& P, double xi, double 
     fy += dy * c;
 }
 
+// Forces of the slots [b, e) of a cell-sorted list on (xi, yi); the lanes of a group take every G-th slot in the same
+// order as a plain `for (s = b + lane; s < e; s += G) acc_force(...)` loop (identical sums), but four neighbour positions
+// are requested before their arithmetic and the four pair chains are independent and branch-free (a slot past the end
+// holds a clamped duplicate and contributes a zero coefficient).  |dx| >= L and fp32 pair terms take the general form.
+__device__ __forceinline__ void range_forces4(const DevParams& P, const double2* __restrict__ sxy, int b, int e, int lane, int G,
+                                              double xi, double yi, double E, double r0sq, double& fx, double& fy) {
+    if (G > 8 || P.precision == 1) {        // wide groups (small systems): a range holds fewer slots than 4 G lanes would take, batching only
+                                            // adds padding; fp32 pair terms: the general form
+        for (int s = b + lane; s < e; s += G) acc_force(P, xi, yi, sxy[s], E, r0sq, fx, fy);
+        return;
+    }
+    const double E12 = 12.0 * E;
+    for (int s = b + lane; s < e; s += 4 * G) {
+        double2 p[4];
+        bool far = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            p[k] = sxy[min(s + k * G, e - 1)];
+            far = far || !(fabs(p[k].x - xi) < P.L);
+        }
+        if (far || P.precision == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (s + k * G < e) acc_force(P, xi, yi, p[k], E, r0sq, fx, fy);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double dx = p[k].x - xi;
+                dx = (dx < 0.0) ? __dadd_rn(dx, P.L) : dx;
+                dx = (dx > P.halfL) ? __dadd_rn(dx, -P.L) : dx;
+                const double dy = p[k].y - yi;
+                const double r2 = dx * dx + dy * dy;
+                const double inv = fast_rcp(r2);
+                const double q2 = r0sq * inv;
+                const double q6 = q2 * q2 * q2;
+                const bool on = (s + k * G < e) && !(r2 < 1e-4);        // r < 1e-2 skipped (Energy.py:55)
+                const double c = on ? E12 * (q6 - q6 * q6) * inv : 0.0;
+                fx += dx * c;
+                fy += dy * c;
+            }
+        }
+    }
+}
+
+// visit_stencil order (Bins.py:76-83) with range_forces4 per contiguous range
+__device__ __forceinline__ void stencil_forces4(const DevParams& P, const CellView& cv, const Stencil& st, int lane, int G,
+                                                double xi, double yi, double E, double r0sq, double& fx, double& fy) {
+    const bool ycontig = (st.ys[0] >= 0) && (st.ys[2] < P.nby) && (st.ys[1] == st.ys[0] + 1) && (st.ys[2] == st.ys[1] + 1);
+    for (int a = 0; a < st.nxs; ++a) {
+        const int cx = st.xs[a];
+        if (cx < 0 || cx >= P.nbx) continue;
+        const int base = cx * P.nby;
+        if (ycontig) {
+            range_forces4(P, cv.sxy, cv.start[base + st.ys[0]], cv.start[base + st.ys[2] + 1], lane, G, xi, yi, E, r0sq, fx, fy);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int cy = st.ys[c];
+                if (cy < 0 || cy >= P.nby) continue;
+                range_forces4(P, cv.sxy, cv.start[base + cy], cv.start[base + cy + 1], lane, G, xi, yi, E, r0sq, fx, fy);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ double pair_energy(const DevParams& P, double xi, double yi, double2 pj, double E, double r0sq) {
     const double dx = put_in_box(pj.x - xi, P.L, P.halfL);
     const double dy = pj.y - yi;

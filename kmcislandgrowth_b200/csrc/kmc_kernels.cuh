@@ -169,9 +169,9 @@ static __global__ void __launch_bounds__(256) k_sweep_forces(DevParams P, CellVi
         if (P.aa_mode == 0) {
             for (int s = lane; s < n; s += G) acc_force(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2, ax, ay);
         } else {
-            visit_stencil(P, ad, st, lane, G, [&](int s) { acc_force(P, pi.x, pi.y, ad.sxy[s], P.E_a, P.ra2, ax, ay); });
+            stencil_forces4(P, ad, st, lane, G, pi.x, pi.y, P.E_a, P.ra2, ax, ay);
         }
-        visit_stencil(P, sub, st, lane, G, [&](int s) { acc_force(P, pi.x, pi.y, sub.sxy[s], P.E_as, P.ras2, sx, sy); });
+        stencil_forces4(P, sub, st, lane, G, pi.x, pi.y, P.E_as, P.ras2, sx, sy);
     }
     ax = group_sum<G>(ax); ay = group_sum<G>(ay);
     sx = group_sum<G>(sx); sy = group_sum<G>(sy);

@@ -21,14 +21,18 @@ static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->timing) { ea = kmc_event_from_pool(c); eb = kmc_event_from_pool(c); cudaEventRecord(ea, c->stream); }
     if (!c->relax2_smem_set) {          // per context (= per device): the staged operands exceed the 48 KB static limit
-        CK(cudaFuncSetAttribute((const void*)k_relax2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
+        CK(cudaFuncSetAttribute((const void*)k_relax2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
+        CK(cudaFuncSetAttribute((const void*)k_relax2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
         c->relax2_smem_set = true;
     }
+    // tall cell grids (configs[4]: 1.6 M cells for 8192 adatoms) take the instantiation whose re-sort walks occupied rows only
+    const bool tall = R.ncell2 > R2_TALL && blocks > 1;
+    void (*kernel)(Relax2Args) = tall ? k_relax2<true> : k_relax2<false>;
     if (R.sync_mode == 1 && !getenv("KMC_CLUSTER1")) {          // one block: a plain launch
-        k_relax2<<<1, R2_THREADS, sizeof(Relax2Smem), c->stream>>>(R);
+        kernel<<<1, R2_THREADS, sizeof(Relax2Smem), c->stream>>>(R);
         CK(cudaGetLastError());
     } else if (R.sync_mode == 0) {
-        CK(cudaLaunchCooperativeKernel((const void*)k_relax2, dim3(blocks), dim3(R2_THREADS), args, sizeof(Relax2Smem), c->stream));
+        CK(cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(R2_THREADS), args, sizeof(Relax2Smem), c->stream));
     } else {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(R2_THREADS); cfg.dynamicSmemBytes = sizeof(Relax2Smem); cfg.stream = c->stream;
@@ -36,7 +40,7 @@ static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = blocks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, k_relax2, R));
+        CK(cudaLaunchKernelEx(&cfg, kernel, R));
     }
     if (c->timing) { cudaEventRecord(eb, c->stream); c->recs.push_back({kmc_family_id(c, "relax_persistent"), ea, eb}); }
     kmc_debug_sync(c, "k_relax2");

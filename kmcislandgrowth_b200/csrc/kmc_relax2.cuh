@@ -312,11 +312,14 @@ __device__ __noinline__ bool relax2_scan_tall(int* a, int m, int* mirror, int* t
 
 // ---- rebuild of the sorted state from `n` source elements (7 barriers; 9 on tall grids) ----------------------
 // src_s / src_oidx may be null (direction 0 / identity index).
+// TALL is a compile-time property of the launch (kmc_relax2.cu picks the instantiation): the common kernel carries none of
+// the tall-grid code (it cost 1 % of the headline when it was a run-time branch).
+template <bool TALL>
 __device__ __forceinline__ bool relax2_rebuild(const Relax2Args& R, const double2* src_pos, const double2* src_s, const int* src_oidx,
                                                double2* dst_pos, double2* dst_s, int* dst_oidx, unsigned int& epoch, Relax2Smem& S, int nA) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const DevParams& P = R.P;
-    const bool tall = R.ncell2 > R2_TALL && gridDim.x > 1;
+    constexpr bool tall = TALL;
     for (int c = gtid; c < R.ncell2; c += gthreads) R.start[c] = 0;
     if (tall) for (int c = gtid; c < P.nbx; c += gthreads) R.colr[c] = make_int2(0x7fffffff, -1);
     if (relax2_barrier(R, epoch)) return true;
@@ -1047,6 +1050,7 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
         t_mark = _t;                                               \
     }
 
+template <bool TALL>
 static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     extern __shared__ __align__(16) unsigned char r2_smem_raw[];
     Relax2Smem& S = *reinterpret_cast<Relax2Smem*>(r2_smem_raw);
@@ -1097,7 +1101,9 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     // at its end, so the control step costs no L2 round trip and no block-wide synchronisation of its own -- the energy
     // phase runs speculatively (it only writes scratch) and the call returns 1 (converged), 2 (restart: stalled or out of
     // bounds) or 3 (line-search cap) BEFORE anything is published.  Returns 0 after a complete line search.
-    auto line_search = [&](bool decide) -> int {
+    // (always_inline: with two call sites the compiler has outlined this lambda in some instantiations, which puts the whole
+    // line-search state on the stack)
+    auto line_search = [&](bool decide) __attribute__((always_inline)) -> int {
         const double dscale = (double)scale;
         const double inv_step = 1.0 / (20.0 * dscale);
         const double2* pos = R.pos[cur];
@@ -1344,7 +1350,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         bool issue_here = false;
         if (rebuild_now) {
             issue_here = true;
-            if (relax2_rebuild(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S, nA)) return 4;
+            if (relax2_rebuild<TALL>(R, posn, sdir, oidx, R.pos[cur], R.sdir[cs ^ 1], R.oidx[cs ^ 1], epoch, S, nA)) return 4;
             if (gtid == 0) *R.need_rebuild = 0;
             if (*R.n_items > R.item_cap) overflow = true;
             ++rebuilds;
@@ -1388,7 +1394,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 R.flag[slot] = mover_flag(P, p, s0, (double)scale);
             }
         } else {
-            if (relax2_rebuild(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S, nA)) { status = -8; break; }
+            if (relax2_rebuild<TALL>(R, R.x0, nullptr, nullptr, R.pos[cur], R.sdir[cs], R.oidx[cs], epoch, S, nA)) { status = -8; break; }
             if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
             relax2_stage_range(R, S, st_min, st_max, er, nA);
             n_items_reg = *R.n_items;
