@@ -108,8 +108,8 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
     R.debug = getenv("KMC_DEBUG_E") ? atoi(getenv("KMC_DEBUG_E")) : 0;
     R.phase_block = !getenv("KMC_PHASE_TIMING") ? -1 : (getenv("KMC_PHASE_BLOCK") ? std::min(atoi(getenv("KMC_PHASE_BLOCK")), blocks - 1) : 0);
     if (R.debug == 8) {      // diagnostics: per-block phase times
-        TRY(slot(c, S_TMP3, (size_t)2 * blocks, &R.blk_ns));
-        CK(cudaMemsetAsync(R.blk_ns, 0, sizeof(unsigned long long) * 2 * blocks, c->stream));
+        TRY(slot(c, S_TMP3, (size_t)3 * blocks, &R.blk_ns));
+        CK(cudaMemsetAsync(R.blk_ns, 0, sizeof(unsigned long long) * 3 * blocks, c->stream));
     }
     const double t_b = kmc_now();
     TRY(launch_relax2(c, R, blocks));
@@ -117,8 +117,8 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
     c->enq_s[2] += t_b - t_a;
     c->enq_s[3] += t_c - t_b;
     if (R.debug == 8) {
-        std::vector<unsigned long long> h(2 * blocks);
-        CK(cudaMemcpyAsync(h.data(), R.blk_ns, sizeof(unsigned long long) * 2 * blocks, cudaMemcpyDeviceToHost, c->stream));
+        std::vector<unsigned long long> h(3 * blocks);
+        CK(cudaMemcpyAsync(h.data(), R.blk_ns, sizeof(unsigned long long) * 3 * blocks, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         for (int ph = 0; ph < 2; ++ph) {
             double mn = 1e30, mx = 0, sum = 0; int arg = 0;
@@ -127,6 +127,9 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
             for (int b = 0; b < blocks; b += 7) fprintf(stderr, " %.0f", (double)h[2 * b + ph] * 1e-3);
             fprintf(stderr, "\n");
         }
+        fprintf(stderr, "[kmc2 per-block G us / smid]");
+        for (int b = 0; b < blocks; ++b) fprintf(stderr, " %d:%.0f/%llu", b, (double)h[2 * b + 1] * 1e-3, h[2 * blocks + b]);
+        fprintf(stderr, "\n");
     }
     // the 512-byte result block travels to the pinned mailbox behind the kernel; the caller synchronises
     TRY(kmc_to_mailbox_async(c, 0, sync, 512));

@@ -1068,6 +1068,11 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     bool stall_check = false;        // the stall test applies from the second line search of a pass on
     bool layout_x0 = false;          // the sorted layout is the one built from x0 and sdir[cs ^ 1] holds F(x0)
     if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); mbar_init(&S.mbar_e, 1); }
+    if (R.debug == 8 && threadIdx.x == 0) {        // diagnostics: which SM runs this block
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        R.blk_ns[2 * gridDim.x + blockIdx.x] = smid;
+    }
     __syncthreads();
     const DevParams& P = R.P;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;

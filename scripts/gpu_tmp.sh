@@ -1,19 +1,19 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 > gpurun_out/r2ab_pytest.log 2>&1; tail -4 gpurun_out/r2ab_pytest.log
-timeout 120 python bench.py --no-cpu > gpurun_out/r2ab_bench1.json 2> gpurun_out/r2ab_bench1.err; python - <<PY
+for i in 1 2; do
+timeout 120 python bench.py --no-cpu > gpurun_out/r2ad_bench$i.json 2> gpurun_out/r2ad_bench$i.err; python - <<PY
 import json
 try:
-    b = json.load(open('gpurun_out/r2ab_bench1.json'))
+    b = json.load(open('gpurun_out/r2ad_bench$i.json'))
     print({k: b[k] for k in ('value', 'us_per_line_search', 'line_searches_per_event', 'gpu_launches')}, b['e2e']['value'], b['roofline']['us_per_line_search_in_kernel'])
 except Exception as e:
-    print('bench failed', e); print(open('gpurun_out/r2ab_bench1.err').read()[-800:])
+    print('bench failed', e); print(open('gpurun_out/r2ad_bench$i.err').read()[-800:])
 PY
-timeout 600 python scripts/bench_sweeps.py > gpurun_out/r2ab_sweeps.jsonl 2> gpurun_out/r2ab_sweeps.err; python - <<'PY'
-import json
-for l in open('gpurun_out/r2ab_sweeps.jsonl'):
-    try: r=json.loads(l)
-    except Exception: continue
-    print(r['workload'], r['precision'], {k:(round(r[k]['us_per_launch'],1), '%.3g'%r[k].get('pair_evals_per_s',0)) for k in ('force_sweep','line_energy_20_candidates','rate_table','select')})
-PY
+done
+KMC_DEBUG_E=9 timeout 120 python bench.py --no-cpu > gpurun_out/r2ad_bench_off.json 2> gpurun_out/r2ad_bench_off.err; python -c "
+import json; b=json.load(open('gpurun_out/r2ad_bench_off.json')); print('plan off', b['value'], b['us_per_line_search'], b['line_searches_per_event'])"
+timeout 300 python scripts/diag_block_times.py 2>&1 | grep -A2 "measured" | cut -c1-600
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 > gpurun_out/r2ad_pytest.log 2>&1; tail -4 gpurun_out/r2ad_pytest.log
+timeout 300 python bench.py --workload cfg5_4096x4096 --no-cpu --steps 10 --warmup 2 --prerelax 20000 > gpurun_out/r2ad_cfg5_single.json 2> gpurun_out/r2ad_cfg5_single.err; python -c "
+import json; b=json.load(open('gpurun_out/r2ad_cfg5_single.json')); print({k:b[k] for k in ('value','us_per_line_search','line_searches_per_event')})"
