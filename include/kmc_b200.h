@@ -230,6 +230,11 @@ int kmc_domain_line_energies(KmcCtx* ctx, const double* xy, const double* dir, i
  * recomputed by the last kmc_rates_update / thresholded kmc_event. */
 int kmc_fp64_peak(KmcCtx* ctx, int32_t repeats, double* tflops_out, double* ms_out);
 int kmc_relax_diag(KmcCtx* ctx, int64_t out[4]);
+/* kmc_barrier_bench: microseconds per device-wide barrier of one 512-thread block per SM that publishes one word per block
+ * (k_relax2 pays three per line search).  variant 0 = the barrier k_relax2 uses (red.release.gpu + ld.acquire.gpu poll by
+ * thread 0 between two bar.sync), variant 1 = hierarchical arrival through thread-block clusters of `cluster` blocks.
+ * stale_out != 0 would mean a block read another block's word of an earlier round (never observed). */
+int kmc_barrier_bench(KmcCtx* ctx, int32_t variant, int32_t cluster, int32_t iters, double* us_out, int32_t* stale_out);
 
 /* The persistent adatom cell list of the trajectory state (replaces the reference's PutInBins of the whole adatom array
  * per neighbour query, Bins.py:91): kmc_rates_update and the thresholded kmc_event edit it in place -- only atoms whose

@@ -94,6 +94,7 @@ SIGNATURES = {
     "kmc_domain_line_energies": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _I32, _I32, _VP, _VP, C.c_int]),
     "kmc_fp64_peak": (C.c_int, [_VP, _I32, C.POINTER(_D), C.POINTER(_D)]),
     "kmc_relax_diag": (C.c_int, [_VP, C.POINTER(_I64)]),
+    "kmc_barrier_bench": (C.c_int, [_VP, _I32, _I32, _I32, C.POINTER(_D), C.POINTER(_I32)]),
     "kmc_cells_stats": (C.c_int, [_VP, C.POINTER(_I64)]),
     "kmc_cells_check": (C.c_int, [_VP, C.POINTER(_I64)]),
 }

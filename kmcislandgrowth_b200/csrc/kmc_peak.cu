@@ -25,7 +25,80 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* __restrict__ out, int
     if (s == 12345.678) out[0] = s;       // never true: keeps the chains alive
 }
 
+// ---- grid-barrier cost (the other denominator of k_relax2: three of these per line search) -------------------------
+// variant 0: the barrier of k_relax2 -- bar.sync, thread 0 arrives with red.release.gpu and polls with ld.acquire.gpu, bar.sync;
+// variant 1: hierarchical -- barrier.cluster inside a thread-block cluster, ONE arrival and ONE poller per cluster, then
+//            barrier.cluster again to release the other blocks of the cluster.
+// Every block also writes and reads one word of data per round (what a real phase boundary has to publish).
+__global__ void __launch_bounds__(512, 1) k_barrier_bench(unsigned int* __restrict__ counter, unsigned int* __restrict__ data, int iters,
+                                                          int variant, int cluster) {
+    unsigned int check = 0;
+    const unsigned int nb = gridDim.x;
+    for (int it = 0; it < iters; ++it) {
+        if (threadIdx.x == 0) data[(it & 1) * 160 + blockIdx.x] = (unsigned int)it;      // double buffered: a block can be one round ahead
+        if (variant == 0) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned int target = (unsigned int)(it + 1) * nb;
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+                unsigned int v;
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
+            }
+            __syncthreads();
+        } else {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+            unsigned int rank;
+            asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+            if (rank == 0 && threadIdx.x == 0) {
+                const unsigned int target = (unsigned int)(it + 1) * (nb / cluster);
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+                unsigned int v;
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
+            }
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        if (threadIdx.x == 0) check += data[(it & 1) * 160 + (blockIdx.x + 1 + it) % nb] - (unsigned int)it;      // another block's word of this round
+    }
+    if (threadIdx.x == 0 && check != 0) data[320] = check;                                           // stale read detected
+}
+
 }  // namespace
+
+// us per grid barrier of `blocks` x 512 threads (one block per SM); variant 1 uses clusters of `cluster` blocks
+extern "C" int kmc_barrier_bench(KmcCtx* c, int32_t variant, int32_t cluster, int32_t iters, double* us_out, int32_t* stale_out) {
+    if (!c || !us_out || iters < 1 || cluster < 1) return kmc_fail(KMC_E_ARG, "bad argument");
+    DevGuard guard(c);
+    int blocks = c->sm_count;
+    if (variant == 1) blocks -= blocks % cluster;
+    unsigned int* buf;
+    TRY(slot(c, S_TMP0, 1024, &buf));
+    TRY(kmc_zero_async(c, buf, 4096));
+    unsigned int* counter = buf;
+    unsigned int* data = buf + 32;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = variant == 1 ? cluster : 1; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = variant == 1 ? 2 : 1;
+    cudaEvent_t e0 = kmc_event_from_pool(c), e1 = kmc_event_from_pool(c);
+    int it = iters, var = variant, cl = cluster;
+    cudaEventRecord(e0, c->stream);
+    CK(cudaLaunchKernelEx(&cfg, k_barrier_bench, counter, data, it, var, cl));
+    cudaEventRecord(e1, c->stream);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    c->event_pool.push_back(e0);
+    c->event_pool.push_back(e1);
+    c->launches++;
+    unsigned int stale = 0;
+    CK(cudaMemcpy(&stale, data + 320, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    if (stale_out) *stale_out = (int32_t)stale;
+    *us_out = (double)ms * 1e3 / iters;
+    return 0;
+}
 
 extern "C" int kmc_fp64_peak(KmcCtx* c, int32_t repeats, double* tflops_out, double* ms_out) {
     if (!c || !tflops_out) return kmc_fail(KMC_E_ARG, "NULL argument");

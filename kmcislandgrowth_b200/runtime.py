@@ -394,6 +394,12 @@ class Context(object):
         check(self.lib.kmc_relax_diag(self.handle, out))
         return {"resorts": int(out[0]), "movers": int(out[1]), "work_items": int(out[2]), "rates_recomputed": int(out[3])}
 
+    def barrier_bench(self, variant=0, cluster=1, iters=20000):
+        """-> (us per device-wide barrier, stale reads seen): variant 0 = k_relax2's barrier, 1 = cluster-hierarchical arrival"""
+        us, stale = C.c_double(0), C.c_int32(0)
+        check(self.lib.kmc_barrier_bench(self.handle, int(variant), int(cluster), int(iters), C.byref(us), C.byref(stale)))
+        return us.value, stale.value
+
     def cells_stats(self):
         """persistent adatom cell list: dict(full_builds, in_place_updates, last_edits, last_check)"""
         out = (C.c_int64 * 4)()
