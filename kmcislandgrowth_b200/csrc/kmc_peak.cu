@@ -45,6 +45,40 @@ __global__ void __launch_bounds__(512, 1) k_barrier_bench(unsigned int* __restri
                 do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
             }
             __syncthreads();
+        } else if (variant == 2) {          // relaxed polls, one acquire fence after the last one
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned int target = (unsigned int)(it + 1) * nb;
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+                unsigned int v;
+                do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            }
+            __syncthreads();
+        } else if (variant == 3) {          // arrivals spread over four counters in four L2 lines, relaxed polls of all four
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned int target = (unsigned int)(it + 1) * nb;
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter + 64 * (blockIdx.x & 3)) : "memory");
+                unsigned int v0, v1, v2, v3;
+                do {
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(counter) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(counter + 64) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(counter + 128) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v3) : "l"(counter + 192) : "memory");
+                } while ((int)(v0 + v1 + v2 + v3 - target) < 0);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            }
+            __syncthreads();
+        } else if (variant == 4) {          // every warp's lane 0 polls for itself: no second bar.sync
+            __syncthreads();
+            const unsigned int target = (unsigned int)(it + 1) * nb;
+            if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+            if ((threadIdx.x & 31) == 0) {
+                unsigned int v;
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
+            }
+            __syncwarp();
         } else {
             asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
             unsigned int rank;
@@ -71,10 +105,10 @@ extern "C" int kmc_barrier_bench(KmcCtx* c, int32_t variant, int32_t cluster, in
     int blocks = c->sm_count;
     if (variant == 1) blocks -= blocks % cluster;
     unsigned int* buf;
-    TRY(slot(c, S_TMP0, 1024, &buf));
-    TRY(kmc_zero_async(c, buf, 4096));
+    TRY(slot(c, S_TMP0, 2048, &buf));
+    TRY(kmc_zero_async(c, buf, 8192));
     unsigned int* counter = buf;
-    unsigned int* data = buf + 32;
+    unsigned int* data = buf + 512;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
     cudaLaunchAttribute attr[2];

@@ -5,7 +5,7 @@ from kmcislandgrowth_b200 import runtime, workloads
 gv = workloads.constants_for(18, 10, 10)
 ctx = runtime.Context(runtime.params_from(gv), 0)
 out = {}
-for variant, cluster in ((0, 1), (1, 2), (1, 4), (1, 8), (0, 1)):
+for variant, cluster in ((0, 1), (2, 1), (3, 1), (4, 1), (1, 2), (1, 4)):
     try:
         ctx.barrier_bench(variant, cluster, 2000)
         us, stale = ctx.barrier_bench(variant, cluster, 50000)
