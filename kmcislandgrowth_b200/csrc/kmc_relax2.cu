@@ -21,13 +21,18 @@ static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->timing) { ea = kmc_event_from_pool(c); eb = kmc_event_from_pool(c); cudaEventRecord(ea, c->stream); }
     if (!c->relax2_smem_set) {          // per context (= per device): the staged operands exceed the 48 KB static limit
-        CK(cudaFuncSetAttribute((const void*)k_relax2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
-        CK(cudaFuncSetAttribute((const void*)k_relax2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
+        CK(cudaFuncSetAttribute((const void*)k_relax2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
+        CK(cudaFuncSetAttribute((const void*)k_relax2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
+        CK(cudaFuncSetAttribute((const void*)k_relax2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
+        CK(cudaFuncSetAttribute((const void*)k_relax2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Relax2Smem)));
         c->relax2_smem_set = true;
     }
     // tall cell grids (configs[4]: 1.6 M cells for 8192 adatoms) take the instantiation whose re-sort walks occupied rows only
     const bool tall = R.ncell2 > R2_TALL && blocks > 1;
-    void (*kernel)(Relax2Args) = tall ? k_relax2<true> : k_relax2<false>;
+    // the diagnostics (KMC_PHASE_TIMING, KMC_DEBUG_E=8) live in instantiations of their own: their timer reads are scheduling
+    // fences that cost the production kernel 4 % even when they never execute
+    const bool timing = R.phase_block >= 0 || R.debug == 8;
+    void (*kernel)(Relax2Args) = tall ? (timing ? k_relax2<true, true> : k_relax2<true, false>) : (timing ? k_relax2<false, true> : k_relax2<false, false>);
     if (R.sync_mode == 1 && !getenv("KMC_CLUSTER1")) {          // one block: a plain launch
         kernel<<<1, R2_THREADS, sizeof(Relax2Smem), c->stream>>>(R);
         CK(cudaGetLastError());

@@ -185,6 +185,7 @@ struct Relax2Smem {
     WorkItem wit[R2_THREADS / 32][R2_WI];    // this block's warps' first work items (static dealing: valid until the next rebuild)
     alignas(8) unsigned long long mbar;      // mbarrier the bulk copy completes on
     alignas(8) unsigned long long mbar_e;    // mbarrier of the energy-phase copies
+    unsigned long long ph[48];               // KMC_PHASE_TIMING: phase times of the observed block, flushed to R.phase_ns at the end
     int smin, smax;
     int emin, emax, submin, submax;
     double e[R2_NE];
@@ -931,13 +932,16 @@ __device__ __forceinline__ double group_sum_rt(double v, int G) {
 
 // Every block owns a contiguous chunk of slots (cell-sorted, so its atoms share one neighbourhood, kept in shared memory).
 // The chunk is processed in ONE pass with T/atoms lanes per atom (see below); larger chunks take several passes.
+template <bool TIMING>
 __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2* pos, double2* sdir, const int* oidx, int mode, double beta,
                                               double scale, bool count_pairs, Relax2Smem& S, unsigned int& parity, int smin, int smax,
                                               bool issue_here, int nA, unsigned long long* tm = nullptr) {
+// (TIMING is a template parameter: the marks are volatile timer reads and act as scheduling fences; compiled into the
+// production kernel -- even never executed -- they cost 4 % of the line search)
 #define GMARK(k)                                                                          \
-    if (tm && threadIdx.x == 0 && blockIdx.x == R.phase_block) {                          \
+    if (TIMING && tm && threadIdx.x == 0 && blockIdx.x == R.phase_block) {                \
         const unsigned long long _t = gtimer();                                           \
-        R.phase_ns[k] += _t - *tm;                                                        \
+        S.ph[k] += _t - *tm;      /* shared memory: a global read-modify-write per mark cost ~0.7 us */ \
         *tm = _t;                                                                         \
     }
     const DevParams& P = R.P;
@@ -1044,13 +1048,13 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
 }
 
 #define PHASE2_MARK(k)                                             \
-    if (threadIdx.x == 0 && blockIdx.x == R.phase_block) {                                               \
+    if (TIMING && threadIdx.x == 0 && blockIdx.x == R.phase_block) {                                     \
         const unsigned long long _t = gtimer();                    \
-        R.phase_ns[k] += _t - t_mark;                              \
+        S.ph[k] += _t - t_mark;                                    \
         t_mark = _t;                                               \
     }
 
-template <bool TALL>
+template <bool TALL, bool TIMING>
 static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     extern __shared__ __align__(16) unsigned char r2_smem_raw[];
     Relax2Smem& S = *reinterpret_cast<Relax2Smem*>(r2_smem_raw);
@@ -1068,7 +1072,8 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     bool stall_check = false;        // the stall test applies from the second line search of a pass on
     bool layout_x0 = false;          // the sorted layout is the one built from x0 and sdir[cs ^ 1] holds F(x0)
     if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); mbar_init(&S.mbar_e, 1); }
-    if (R.debug == 8 && threadIdx.x == 0) {        // diagnostics: which SM runs this block
+    if (TIMING && threadIdx.x < 48) S.ph[threadIdx.x] = 0ull;
+    if (TIMING && R.debug == 8 && threadIdx.x == 0) {        // diagnostics: which SM runs this block
         unsigned int smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         R.blk_ns[2 * gridDim.x + blockIdx.x] = smid;
@@ -1090,7 +1095,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
     bool first_pass = true;
     bool overflow = false;
     long long rebuilds = 0, mover_sum = 0;
-    unsigned long long t_mark = gtimer();
+    unsigned long long t_mark = TIMING ? gtimer() : 0ull;
 
     // request the operands of an energy phase: positions, directions and mover flags of slots [emin, emax)
     auto issue_e = [&](const double2* p, const double2* d) {
@@ -1116,7 +1121,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         double2* sdir = R.sdir[cs];
         const int* oidx = R.oidx[cs];
         // ---------------- E
-        unsigned long long t_blk = (R.debug == 8 && threadIdx.x == 0) ? gtimer() : 0ull;
+        unsigned long long t_blk = (TIMING && R.debug == 8 && threadIdx.x == 0) ? gtimer() : 0ull;
         double mfv[5];                          // this lane's share of the max|F|^2 partials (grids have at most 160 blocks)
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -1228,7 +1233,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             R.partial[(size_t)threadIdx.x * nblk + blockIdx.x] = v;
         }
         PHASE2_MARK(0)
-        if (R.debug == 8 && threadIdx.x == 0) R.blk_ns[2 * blockIdx.x] += gtimer() - t_blk;
+        if (TIMING && R.debug == 8 && threadIdx.x == 0) R.blk_ns[2 * blockIdx.x] += gtimer() - t_blk;
         if (relax2_barrier(R, epoch)) return 4;
         PHASE2_MARK(1)
         // ---------------- F
@@ -1318,7 +1323,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
         PHASE2_MARK(3)
         if (relax2_barrier(R, epoch)) return 4;
         PHASE2_MARK(4)
-        if (R.debug == 8 && threadIdx.x == 0) t_blk = gtimer();
+        if (TIMING && R.debug == 8 && threadIdx.x == 0) t_blk = gtimer();
         // x_np is published: fetch this block's neighbourhood [st_min, st_max) (two elements per thread) together with
         // the beta partials -- ONE L2 round trip, one __syncthreads -- into shared memory for the force sweep.
         // (A TMA bulk copy of the same ~5 KB took ~1.9 us from issue to completion here; plain loads take ~0.7 us.)
@@ -1367,9 +1372,9 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             cur ^= 1;
         }
         PHASE2_MARK(11)
-        relax2_forces(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, tma_parity, st_min, st_max, issue_here, nA, &t_mark);
+        relax2_forces<TIMING>(R, R.pos[cur ^ 1], R.sdir[cs], R.oidx[cs], 1, beta, dscale, false, S, tma_parity, st_min, st_max, issue_here, nA, &t_mark);
         PHASE2_MARK(5)
-        if (R.debug == 8 && threadIdx.x == 0) R.blk_ns[2 * blockIdx.x + 1] += gtimer() - t_blk;
+        if (TIMING && R.debug == 8 && threadIdx.x == 0) R.blk_ns[2 * blockIdx.x + 1] += gtimer() - t_blk;
         if (relax2_barrier(R, epoch)) return 4;
         PHASE2_MARK(6)
         // the next line search (if there is one) starts from x_np with the directions and flags just published: request
@@ -1403,7 +1408,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             if (*R.n_items > R.item_cap) { status = -4; break; }            // work list too small: the host grows it and relaunches
             relax2_stage_range(R, S, st_min, st_max, er, nA);
             n_items_reg = *R.n_items;
-            relax2_forces(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true, nA);   // dx0, sn = dx0  :120,125
+            relax2_forces<TIMING>(R, R.pos[cur], R.sdir[cs], R.oidx[cs], 0, 0.0, (double)scale, first_pass, S, tma_parity, st_min, st_max, true, nA);   // dx0, sn = dx0  :120,125
             first_pass = false;
             __syncthreads();
             for (int slot = lo + threadIdx.x; slot < hi; slot += R2_THREADS) R.sdir[cs ^ 1][slot] = R.sdir[cs][slot];     // dx0, kept for the restarts
@@ -1437,6 +1442,9 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             R.x0[oidx[slot]] = p;
         }
     }
+    if (TIMING && (int)blockIdx.x == R.phase_block && threadIdx.x == 0)
+        for (int k = 0; k < 48; ++k)
+            if (k != 8 && k != 9) R.phase_ns[k] = S.ph[k];
     if (gtid == 0) {
         R.stats->line_searches = ls;
         R.stats->restarts = restarts;
