@@ -122,9 +122,13 @@ struct Relax2Args {
 // and falls through as well, the line search returns, and the launch ends with status KMC_E_TIMEOUT instead of hanging
 // the device (a hung cooperative kernel can only be removed by resetting the GPU).
 constexpr unsigned long long R2_SPIN_NS = 4000000000ull;
-__device__ __forceinline__ bool relax2_spin_expired(const Relax2Args& R, unsigned long long t0, int who) {
+// (the timer is first read after the first batch of failed polls, t0 == 0 meaning "not started": a timer read on the fast
+// path of every barrier and copy wait is a volatile instruction the scheduler cannot move work across)
+__device__ __forceinline__ bool relax2_spin_expired(const Relax2Args& R, unsigned long long& t0, int who) {
     if (*(volatile int*)R.abort != 0) return true;
-    if (gtimer() - t0 > R2_SPIN_NS) { atomicCAS(R.abort, 0, who); return true; }
+    const unsigned long long now = gtimer();
+    if (t0 == 0ull) { t0 = now; return false; }
+    if (now - t0 > R2_SPIN_NS) { atomicCAS(R.abort, 0, who); return true; }
     return false;
 }
 // returns true (block-uniform) when the watchdog fired
@@ -144,7 +148,7 @@ __device__ __forceinline__ bool relax2_barrier(const Relax2Args& R, unsigned int
             const unsigned int target = (epoch + 1u) * gridDim.x;
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(R.barrier) : "memory");
             unsigned int v;
-            const unsigned long long t0 = gtimer();
+            unsigned long long t0 = 0ull;
             unsigned int spins = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(R.barrier) : "memory");
@@ -280,13 +284,15 @@ __device__ __noinline__ bool relax2_scan_tall(int* a, int m, int* mirror, int* t
         const unsigned int target = (epoch + 1u) * gridDim.x;
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
         unsigned int v;
-        const unsigned long long t0 = gtimer();
+        unsigned long long t0 = 0ull;
         unsigned int spins = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
             if ((++spins & 1023u) == 0) {
                 if (*(volatile int*)abortw != 0) { dead = true; break; }
-                if (gtimer() - t0 > R2_SPIN_NS) { atomicCAS(abortw, 0, 1); dead = true; break; }
+                const unsigned long long now = gtimer();
+                if (t0 == 0ull) t0 = now;
+                else if (now - t0 > R2_SPIN_NS) { atomicCAS(abortw, 0, 1); dead = true; break; }
             }
         } while ((int)(v - target) < 0);
     }
@@ -795,7 +801,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(const Relax2Args& R, unsigned long long* bar, unsigned int parity) {
-    const unsigned long long t0 = gtimer();
+    unsigned long long t0 = 0ull;
     unsigned int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if ((++spins & 255u) == 0 && relax2_spin_expired(R, t0, 3)) break;
