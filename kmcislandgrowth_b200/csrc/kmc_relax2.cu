@@ -31,7 +31,7 @@ static int launch_relax2(KmcCtx* c, Relax2Args& R, int blocks) {
     const bool tall = R.ncell2 > R2_TALL && blocks > 1;
     // the diagnostics (KMC_PHASE_TIMING, KMC_DEBUG_E=8) live in instantiations of their own: their timer reads are scheduling
     // fences that cost the production kernel 4 % even when they never execute
-    const bool timing = R.phase_block >= 0 || R.debug == 8;
+    const bool timing = R.phase_block >= 0 || R.debug == 8 || R.debug == 7;
     void (*kernel)(Relax2Args) = tall ? (timing ? k_relax2<true, true> : k_relax2<true, false>) : (timing ? k_relax2<false, true> : k_relax2<false, false>);
     if (R.sync_mode == 1 && !getenv("KMC_CLUSTER1")) {          // one block: a plain launch
         kernel<<<1, R2_THREADS, sizeof(Relax2Smem), c->stream>>>(R);

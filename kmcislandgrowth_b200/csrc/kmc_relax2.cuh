@@ -615,7 +615,6 @@ __device__ __forceinline__ PairGeo relax2_round_geo(const DevParams& P, const Pa
 __device__ __forceinline__ void relax2_round_compute(const Relax2Args& R, const PairLoad& L, double inv_step, int lane, double (&acc)[PD + 1], double& eslow) {
     const DevParams& P = R.P;
     const PairGeo g = relax2_round_geo(P, L, inv_step);
-    if (R.debug == 1) { if (g.valid) acc[0] += g.dx0 + g.dy0 + g.ddx + g.ddy; return; }
     relax2_pair_round(P, g.valid, g.dx0, g.dy0, g.ddx, g.ddy, g.is_sub, lane, acc, eslow);
 }
 // two rounds at once: their polynomial chains are independent and interleave
@@ -623,7 +622,6 @@ __device__ __forceinline__ void relax2_round_compute2(const Relax2Args& R, const
                                                       double (&acc)[PD + 1], double& eslow) {
     const DevParams& P = R.P;
     const PairGeo ga = relax2_round_geo(P, LA, inv_step), gb = relax2_round_geo(P, LB, inv_step);
-    if (R.debug == 1) { if (ga.valid) acc[0] += ga.dx0 + ga.dy0 + ga.ddx + ga.ddy; if (gb.valid) acc[0] += gb.dx0 + gb.dy0 + gb.ddx + gb.ddy; return; }
     const PolyPrep ra = pair_line_prep(P, ga.valid, ga.dx0, ga.dy0, ga.ddx, ga.ddy, ga.is_sub ? P.E_as : P.E_a, ga.is_sub ? P.inv_ras2 : P.inv_ra2);
     const PolyPrep rb = pair_line_prep(P, gb.valid, gb.dx0, gb.dy0, gb.ddx, gb.ddy, gb.is_sub ? P.E_as : P.E_a, gb.is_sub ? P.inv_ras2 : P.inv_ra2);
     if (__all_sync(0xffffffffu, (!ra.ok || ra.small) && (!rb.ok || rb.small))) {       // warp-uniform choice of the degree
@@ -1033,8 +1031,8 @@ __device__ __forceinline__ void relax2_forces(const Relax2Args& R, const double2
                 sn = make_double2(__dadd_rn(fx, __dmul_rn(beta, so.x)), __dadd_rn(fy, __dmul_rn(beta, so.y)));   // :147
             }
             sdir[slot] = sn;
-            R.flag[slot] = (R.debug == 4) ? 0 : mover_flag(P, pi, sn, scale);
-            if (R.debug == 7) {
+            R.flag[slot] = mover_flag(P, pi, sn, scale);
+            if (TIMING && R.debug == 7) {
                 const double d = sqrt(sn.x * sn.x + sn.y * sn.y) * (double)(KC - 1) / (20.0 * scale);
                 int b = (int)floor(2.0 * (log10(fmax(d, 1e-30)) + 6.0));       // half decades from 1e-6
                 b = max(0, min(15, b));
@@ -1186,7 +1184,7 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 O.pos = S.epos - er.emin; O.dir = S.edir - er.emin; O.flag = S.eflag - er.emin;
             }
             if (er.submax > er.submin) O.sub = S.esub - er.submin;
-            if (R.debug != 2) relax2_items(R, S.wit[warp], er.kb + warp, wpb, er.ke, O, inv_step, lane, acc, eslow);
+            relax2_items(R, S.wit[warp], er.kb + warp, wpb, er.ke, O, inv_step, lane, acc, eslow);
         }
         if (P.aa_mode == 0) {
             for (int i = gwarp; i < nA; i += nwarps) {
