@@ -1282,7 +1282,10 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
             }
         }
         __syncthreads();
-        if (warp == 0) {        // candidate energies = polynomial + per-candidate sums; first argmin (2DGrowth.py:123,155)
+        int amin;
+        {   // candidate energies = polynomial + per-candidate sums; first argmin (2DGrowth.py:123,155).  EVERY warp forms it from
+            // the same shared sums with the same butterfly (identical result in every lane of every warp): no second block
+            // synchronisation, no warp-0 section the other fifteen warps wait for
             double ev = INFINITY;
             int ai = lane;
             if (lane < KC) ev = poly_at(S.e + KC, lane) + S.e[lane];
@@ -1292,10 +1295,8 @@ static __global__ void __launch_bounds__(R2_THREADS, 1) k_relax2(Relax2Args R) {
                 const int oi = __shfl_xor_sync(0xffffffffu, ai, o);
                 if (ov < ev || (ov == ev && oi < ai)) { ev = ov; ai = oi; }
             }
-            if (lane == 0) S.amin = ai;
+            amin = ai;
         }
-        __syncthreads();
-        const int amin = S.amin;
         double top = 0.0, bot = 0.0, my = INFINITY;
         for (int slot = myslot; slot < hi; slot += R2_THREADS) {
             const bool first = slot == myslot;
