@@ -108,6 +108,7 @@ int kmc_relax2_enqueue(KmcCtx* c, const KmcBins* sb, int32_t scale0, double thre
     R.pair_counter = (unsigned long long*)(sync + 32);
     R.stats = (KmcRelaxStatsDev*)(sync + 64);
     R.phase_ns = (unsigned long long*)(sync + 128);
+    R.hist = (unsigned long long*)(sync + 256);          // KMC_DEBUG_E=7 (shares the words of the unused phase slots 16-31)
     R.scale0 = scale0; R.threshold0 = threshold0; R.max_ls = max_ls;
     R.sync_mode = sync_mode;
     R.debug = getenv("KMC_DEBUG_E") ? atoi(getenv("KMC_DEBUG_E")) : 0;
