@@ -486,6 +486,20 @@ def test_incremental_rate_table_touches_only_the_neighbourhood():
         ctx.close()
 
 
+def test_grid_barrier_microbenchmark_publishes_data():
+    """kmc_barrier_bench: every variant of the device-wide barrier must order the blocks' writes (no stale read of another
+    block's word), and the barrier k_relax2 uses must cost microseconds, not milliseconds (profiles/r2_barrier_microbench.md)."""
+    from kmcislandgrowth_b200 import runtime, workloads
+    ctx = runtime.Context(runtime.params_from(workloads.constants_for(18, 10, 10)), 0)
+    try:
+        for variant, cluster in ((0, 1), (1, 2), (2, 1), (3, 1)):
+            us, stale = ctx.barrier_bench(variant, cluster, 3000)
+            assert stale == 0, (variant, cluster, stale)
+            assert 0.2 < us < 50.0, (variant, cluster, us)
+    finally:
+        ctx.close()
+
+
 def Periodic_wrap(x, L):
     """Periodic.py:8-20 for one coordinate"""
     x = x % L
